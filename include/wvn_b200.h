@@ -1,0 +1,213 @@
+/* wvn-b200 — C ABI of libwvn_b200.so
+ *
+ * B200-native (sm_100a) implementation of the Wild Visual Navigation per-frame hot path:
+ * DINO ViT forward -> STEGO segmentation head / per-segment feature gather -> traversability
+ * MLP (per-pixel inference with confidence, and the online train step).
+ *
+ * The reference (leggedrobotics/wild_visual_navigation @ 8b9caf9) is pure Python and has no
+ * FFI for this path: its boundary is the Python class surface
+ * (FeatureExtractor / DinoInterface / StegoInterface / SegmentExtractor / SimpleMLP /
+ * TraversabilityLoss / ConfidenceGenerator / TraversabilityEstimator).  The entry points
+ * below are what a ctypes binding inside those classes calls; each cites the reference
+ * code it replaces (paths relative to the reference repository root).  INTEGRATION.md shows
+ * the reference-side stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless named host_*; tensors are dense, row-major;
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *  - functions return 0 on success, a negative wvn_status otherwise; wvn_last_error() gives
+ *    the message for the calling thread;
+ *  - no ownership transfer; handles own their weights and workspaces (allocated at create,
+ *    nothing is allocated on the per-frame path);
+ *  - a handle must not be used from two host threads at once (the reference serialises
+ *    frames through its Scheduler and training through `_learning_lock`).
+ */
+#ifndef WVN_B200_H_
+#define WVN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  WVN_STATUS_OK = 0,
+  WVN_STATUS_INVALID = -1,   /* bad argument / unsupported shape */
+  WVN_STATUS_CUDA = -2,      /* CUDA error, see wvn_last_error() */
+  WVN_STATUS_NO_DEVICE = -3, /* no sm_100 device visible */
+  WVN_STATUS_STATE = -4      /* handle not ready (e.g. a weight was never set) */
+} wvn_status;
+
+const char* wvn_last_error(void);
+/* 0 if device 0..n has compute capability 10.x, WVN_STATUS_NO_DEVICE otherwise. */
+int wvn_check_device(void);
+int wvn_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Primitive: bf16 tensor-core GEMM  C = A[M,K] * W[N,K]^T  (tcgen05, fp32 accumulate)
+ * Replaces every nn.Linear / 1x1-conv call of the path (cuBLAS in the reference).
+ * out_kind: 0 = bf16 out[M,ldo] = act(acc + bias); 1 = fp32 out = acc + bias;
+ *           2 = fp32 out += acc + bias (residual).   act: 0 none, 1 ReLU, 2 GELU(erf).
+ * K % 64 == 0, N % block_n == 0, block_n in {0 (auto), 64, 128, 192, 224, 256}.
+ * ---------------------------------------------------------------------------------------- */
+int wvn_gemm_bf16(const void* a_bf16, long long lda, const void* w_bf16, const float* bias, void* out, long long ldo,
+                  int m, int n, int k, int out_kind, int act, int block_n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Primitive: fused multi-head attention, head dim 64, non-causal.
+ * Replaces `softmax(q @ k.transpose(-2,-1) * scale) @ v` of the DINO ViT block
+ * ([EXTERNAL] stego/backbones/dino/vision_transformer.py Attention.forward).
+ * q,k: [batch*heads, npad, 64] bf16; vt: [batch*heads, 64, npad] bf16;
+ * out: [batch, npad, heads*64] bf16.  Keys >= n_valid are masked.  npad % 128 == 0.
+ * ---------------------------------------------------------------------------------------- */
+int wvn_attention_bf16(const void* q, const void* k, const void* vt, void* out, int batch, int heads, int npad,
+                       int n_valid, float scale, void* stream);
+
+/* LayerNorm over fp32 rows -> bf16 (and/or fp32) rows; dim in {384, 768}. */
+int wvn_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int dim,
+                  float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ViT backbone handle — replaces DinoInterface.__init__/inference's backbone
+ * (wild_visual_navigation/feature_extractor/dino_interface.py:16-59, :70-92 and the
+ *  [EXTERNAL] stego.backbones.backbone.get_backbone -> DINO VisionTransformer).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct wvn_vit wvn_vit_t;
+
+typedef struct {
+  int image_size;   /* side of the (square) network input after resize + center crop, e.g. 448 */
+  int patch_size;   /* 8 or 16 */
+  int dim;          /* 384 (vit_small) or 768 (vit_base) */
+  int depth;        /* 12 */
+  int heads;        /* dim / 64 */
+  int mlp_dim;      /* 4 * dim */
+  int max_batch;    /* largest batch a single forward call may carry */
+  int chunk;        /* frames processed together (activations stay L2-resident); 0 = default */
+  float ln_eps;     /* 1e-6 */
+  int head_out;     /* columns of the STEGO head output matrix (multiple of 64), 0 = no head */
+} wvn_vit_config;
+
+int wvn_vit_create(const wvn_vit_config* cfg, wvn_vit_t** out);
+void wvn_vit_destroy(wvn_vit_t* h);
+
+/* Weights use the DINO state-dict names (fp32, host or device memory):
+ *   cls_token [dim], pos_embed [(1+P), dim] (already interpolated to this token grid),
+ *   patch_embed.proj.weight [dim, 3*p*p], patch_embed.proj.bias [dim],
+ *   blocks.{i}.norm1.{weight,bias}, blocks.{i}.attn.qkv.{weight [3dim,dim],bias},
+ *   blocks.{i}.attn.proj.{weight,bias}, blocks.{i}.norm2.{weight,bias},
+ *   blocks.{i}.mlp.fc1.{weight [mlp,dim],bias}, blocks.{i}.mlp.fc2.{weight [dim,mlp],bias},
+ *   norm.{weight,bias}
+ * and for the STEGO head (see wvn_vit_stego_head):
+ *   stego.head_a.weight [head_out, dim], stego.head_a.bias [head_out],
+ *   stego.hidden.weight [dim, dim], stego.hidden.bias [dim], stego.head_b.weight [head_out, dim]. */
+int wvn_vit_set_weight(wvn_vit_t* h, const char* name, const float* data, long long numel);
+
+/* img: [batch, 3, in_h, in_w] fp32 in [0,1].  Applies the interface's transform
+ * (Resize(image_size, NEAREST) + CenterCrop(image_size) + ImageNet Normalize,
+ *  dino_interface.py:52-59) inside the patch loader, runs the backbone, and writes the final
+ * LayerNorm output of the patch tokens (CLS dropped): tokens_out [batch, P, dim] fp32.
+ * resized_h/resized_w: size after the virtual NEAREST resize (== in_h/in_w when no resize). */
+int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_w, int resized_h, int resized_w,
+                    float* tokens_out, void* stream);
+
+/* STEGO segmentation head on the tokens of the last forward
+ * (stego_interface.py:91-100; [EXTERNAL] stego.stego.Stego.forward / cluster & linear probes):
+ *   out[row, :] = head_a(t) + head_b(relu(hidden(t)))           out: [batch*npad, head_out] fp32
+ * where the caller stacks code / cluster-probe / linear-probe rows into head_a / head_b.
+ * Row b*npad + 1 + p holds patch p of frame b (row b*npad is the CLS token). */
+int wvn_vit_stego_head(wvn_vit_t* h, int batch, float* out, void* stream);
+int wvn_vit_npad(const wvn_vit_t* h);
+
+/* ------------------------------------------------------------------------------------------
+ * Token grid -> image resolution
+ * ---------------------------------------------------------------------------------------- */
+/* F.interpolate(features, (out,out), "bilinear", align_corners=True) (dino_interface.py:87-90).
+ * tokens: [batch, gh*gw, dim] fp32 -> out: [batch, dim, out_h, out_w] fp32. */
+int wvn_upsample_dense(const float* tokens, float* out, int batch, int dim, int gh, int gw, int out_h, int out_w,
+                       void* stream);
+/* bilinear (align_corners=False) upsampling of per-patch logits + argmax -> int64 segment ids
+ * (STEGO postprocess + stego_interface.py:108-109).  logits: [batch*npad, ld] fp32. */
+int wvn_logits_argmax(const float* logits, long long ld, int col0, int classes, int batch, int npad, int gh, int gw,
+                      int out_h, int out_w, long long* seg, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Segment reductions — replace SegmentExtractor.adjacency_list / .centers
+ * (feature_extractor/segment_extractor.py:40-92), FeatureExtractor.sparsify_features
+ * (feature_extractor.py:389-396) and the relabel loop of segment_stego (:245-246).
+ * ---------------------------------------------------------------------------------------- */
+size_t wvn_segment_workspace_bytes(int batch, int smax, int gh, int gw);
+/* seg: [batch, h, w] int64 with ids in [0, smax) (others ignored).
+ * feat: [batch, smax, dim] fp32 or NULL (needs tokens [batch, gh*gw, dim] fp32);
+ * centers: [batch, smax, 2] fp32 (x=col, y=row) or NULL;
+ * edges: [batch, max_edges, 2] int64 (le, ri) sorted like torch.unique of the reference's keys,
+ * n_edges: [batch] int32; both NULL to skip. */
+int wvn_segment_reduce(const long long* seg, int batch, int h, int w, int smax, const float* tokens, int gh, int gw,
+                       int dim, float* feat, float* centers, long long* edges, int* n_edges, int max_edges,
+                       void* workspace, void* stream);
+/* In-place relabel of each frame to 0..S-1; scratch: [batch*num_labels] int32; counts: [batch] int32. */
+int wvn_segment_relabel(long long* seg, int batch, long long pix_per_frame, int num_labels, int* scratch, int* counts,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Traversability MLP inference over every pixel — replaces
+ *   x = dense_feat[0].permute(1,2,0).reshape(-1, D); prediction = model.forward(Data(x));
+ *   out_trav = prediction[...,0]; loss_reco = mse(prediction[:,1:], x).mean(1);
+ *   confidence = confidence_generator.inference_without_update(loss_reco)
+ * (wild_visual_navigation_ros/scripts/wvn_feature_extractor_node.py:319-370,
+ *  model/simple_mlp.py:33-39, utils/confidence_generator.py:182-193).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct wvn_mlp_infer wvn_mlp_infer_t;
+int wvn_mlp_infer_create(int dim, int h1, int h2, int chunk_rows, wvn_mlp_infer_t** out);
+void wvn_mlp_infer_destroy(wvn_mlp_infer_t* h);
+/* params: flat fp32 buffer in state_dict order layers.0.weight, layers.0.bias, layers.2.weight,
+ * layers.2.bias, layers.4.weight, layers.4.bias (device memory). */
+int wvn_mlp_infer_set_params(wvn_mlp_infer_t* h, const float* params, void* stream);
+/* tokens: [batch, gh*gw, dim] fp32; trav, conf: [batch, out_h, out_w] fp32;
+ * cg_mean, cg_std: device scalars of the ConfidenceGenerator. */
+int wvn_mlp_infer_pixels(wvn_mlp_infer_t* h, const float* tokens, int batch, int gh, int gw, int out_h, int out_w,
+                         const float* cg_mean, const float* cg_std, float std_factor, float* trav, float* conf,
+                         void* stream);
+/* Same arithmetic on explicit rows x: [rows, dim] fp32 (segment-wise prediction mode). */
+int wvn_mlp_infer_rows(wvn_mlp_infer_t* h, const float* x, long long rows, const float* cg_mean,
+                       const float* cg_std, float std_factor, float* trav, float* conf, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Online train step (fp32) — replaces the body of TraversabilityEstimator.train()
+ * (traversability_estimator/traversability_estimator.py:464-477): SimpleMLP.forward,
+ * TraversabilityLoss.forward (utils/loss.py:93-160) with the ConfidenceGenerator
+ * "latest_measurement" update (utils/confidence_generator.py:78-82), backward, Adam.
+ * Three phases so a data-parallel caller can all-reduce between them:
+ *   forward_stats -> [all-reduce scalars[0..4] (5 doubles)] -> backward
+ *   -> [all-reduce grads (n_params + 1 floats)] -> finalize + adam.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  float w_trav, w_reco, std_factor;
+  int anomaly_balanced;
+  float lr, beta1, beta2, eps;
+} wvn_train_config;
+
+size_t wvn_mlp_param_count(int dim, int h1, int h2);
+size_t wvn_mlp_train_workspace_bytes(int dim, int h1, int h2, int max_rows);
+size_t wvn_mlp_train_scalars_bytes(void);
+int wvn_mlp_train_forward_stats(int dim, int h1, int h2, const float* params, const float* x, const float* y,
+                                const unsigned char* y_valid, int rows, int max_rows, void* workspace, void* scalars,
+                                void* stream);
+int wvn_mlp_train_backward(int dim, int h1, int h2, const float* params, const float* x, const float* y,
+                           const unsigned char* y_valid, int rows, int max_rows, long long n_total,
+                           const wvn_train_config* cfg, void* workspace, void* scalars, float* cg_mean, float* cg_std,
+                           float* grads, float* confidence_out, void* stream);
+int wvn_mlp_train_apply(int dim, int h1, int h2, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                        long long* step_counter, long long n_total, const wvn_train_config* cfg, void* scalars,
+                        void* stream);
+/* metrics_out (device, 6 floats): loss_total, loss_trav, loss_reco, loss_trav_confidence, cg_mean, cg_std */
+int wvn_mlp_train_read_metrics(const void* scalars, float* metrics_out, void* stream);
+/* fp32 forward only: out [rows, 1+dim] (column 0 through the sigmoid), SimpleMLP.forward. */
+int wvn_mlp_forward_f32(int dim, int h1, int h2, const float* params, const float* x, int rows, float* h1_buf,
+                        float* h2_buf, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WVN_B200_H_ */

@@ -1,0 +1,310 @@
+// wvn-b200: fused non-causal multi-head attention (flash-style) on tcgen05, head dim 64.
+//
+// Replaces the materialised `softmax(q @ k^T * scale) @ v` of the DINO ViT blocks
+// (SURVEY.md §8 a3 / K4): per (frame, head) the 3137x3137 (ViT-S/8 @448) score matrix is
+// never written to HBM; S lives in tensor memory, P goes through shared memory straight
+// back into the tensor core, O accumulates in tensor memory.
+//
+// Inputs (written by the QKV GEMM epilogue, bf16):
+//   Q, K : [B*H, npad, 64]   row-major (K-major for the MMA)
+//   V^T  : [B*H, 64, npad]   row-major (so P·V also sees a K-major B operand)
+// Output: O [B, npad, H*64] bf16 (the layout the out-projection GEMM reads).
+//
+// One CTA = one 128-row query tile of one (frame, head); 2 CTAs are co-resident per SM so
+// the tensor core works on one CTA's MMAs while the other CTA is in its softmax phase.
+//   warp 0    : TMEM alloc, then TMA producer (Q once; K / V^T tiles, 2 stages each)
+//   warp 1    : MMA issuer  (S = Q K^T : 4 x UMMA 128x128x16;  O += P V : 8 x UMMA 128x64x16)
+//   warps 2-5 : softmax (1 thread = 1 query row): tcgen05.ld S, online softmax with lazy
+//               rescaling, P -> bf16 -> swizzled smem, final O / l epilogue.
+#include "attention.h"
+#include "common.cuh"
+#include "host_common.h"
+
+namespace wvn {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kTileQ = 128;
+constexpr int kTileKV = 128;
+constexpr int kDh = 64;
+constexpr uint32_t kQBytes = kTileQ * kDh * 2;       // 16 KB
+constexpr uint32_t kKBytes = kTileKV * kDh * 2;      // 16 KB
+constexpr uint32_t kVBytes = kDh * kTileKV * 2;      // 16 KB (two 8 KB K-blocks)
+constexpr uint32_t kPBytes = kTileQ * kTileKV * 2;   // 32 KB (two 16 KB K-blocks)
+constexpr int kStages = 2;
+constexpr uint32_t kOffQ = 0;
+constexpr uint32_t kOffK = kOffQ + kQBytes;
+constexpr uint32_t kOffV = kOffK + kStages * kKBytes;
+constexpr uint32_t kOffP = kOffV + kStages * kVBytes;
+constexpr uint32_t kOffBar = kOffP + kPBytes;
+constexpr uint32_t kSmemBytes = kOffBar + 256;
+constexpr uint32_t kTmemCols = 256;  // S: [0,128)  O: [128,192)
+constexpr uint32_t kColS = 0;
+constexpr uint32_t kColO = 128;
+constexpr float kRescaleThreshold = 8.0f;  // in log2 units (FA4-style lazy rescale)
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_vt, const AttnArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_empty = bars + 3;  // [2]
+  uint64_t* v_full = bars + 5;   // [2]
+  uint64_t* v_empty = bars + 7;  // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_free = bars + 10;
+  uint64_t* p_full = bars + 11;
+  uint64_t* pv_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x;
+  const int bh = blockIdx.y;
+  const int nkv = args.npad / kTileKV;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("[wvn] attention: dynamic smem base not 1024B aligned\n");
+    __trap();
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // -------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_q);
+      tma_prefetch_desc(&tmap_k);
+      tma_prefetch_desc(&tmap_vt);
+      const int row0 = bh * args.npad;
+      mbar_arrive_expect_tx(q_full, kQBytes);
+      tma_load_2d(&tmap_q, q_full, smem + kOffQ, 0, row0 + q_tile * kTileQ);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], kKBytes);
+        tma_load_2d(&tmap_k, &k_full[st], smem + kOffK + st * kKBytes, 0, row0 + j * kTileKV);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], kVBytes);
+        tma_load_2d(&tmap_vt, &v_full[st], smem + kOffV + st * kVBytes, j * kTileKV, bh * kDh);
+        tma_load_2d(&tmap_vt, &v_full[st], smem + kOffV + st * kVBytes + kVBytes / 2, j * kTileKV + 64, bh * kDh);
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV);  // 128 x 128
+      constexpr uint32_t idesc_o = make_idesc_bf16(kTileQ, kDh);      // 128 x 64
+      const uint32_t tmem_s = tmem_base + kColS;
+      const uint32_t tmem_o = tmem_base + kColO;
+      const uint64_t desc_q = make_sw128_kmajor_desc(smem_u32(smem + kOffQ));
+
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_full[st], ph);
+        if (j > 0) mbar_wait(s_free, (j - 1) & 1);  // softmax has drained S(j-1) from TMEM
+        tc_fence_after();
+        const uint64_t desc_k = make_sw128_kmajor_desc(smem_u32(smem + kOffK + st * kKBytes));
+#pragma unroll
+        for (int k = 0; k < kDh / 16; ++k) umma_bf16_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc_s, k != 0);
+        umma_commit(&k_empty[st]);
+        umma_commit(s_full);
+      };
+
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) issue_qk(j + 1);  // overlaps softmax(j)'s tail and P(j) hand-off
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[st], ph);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(smem + kOffP);
+        const uint32_t v_addr = smem_u32(smem + kOffV + st * kVBytes);
+#pragma unroll
+        for (int ks = 0; ks < kTileKV / 16; ++ks) {
+          const uint64_t desc_p = make_sw128_kmajor_desc(p_addr + (ks >> 2) * (kPBytes / 2)) + 2 * (ks & 3);
+          const uint64_t desc_v = make_sw128_kmajor_desc(v_addr + (ks >> 2) * (kVBytes / 2)) + 2 * (ks & 3);
+          umma_bf16_ss(tmem_o, desc_p, desc_v, idesc_o, (j | ks) != 0);
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- softmax / correction / epilogue
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // row inside the query tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tmem_s = tmem_base + lane_base + kColS;
+    const uint32_t tmem_o = tmem_base + lane_base + kColO;
+    uint8_t* p_row = smem + kOffP + row * 128;
+    const int sw = row & 7;
+    const float sl2 = args.scale_log2;
+
+    float m_ref = -INFINITY;  // running reference max (raw score units)
+    float l = 0.f;            // running sum of exp2((s - m_ref) * sl2)
+
+    for (int j = 0; j < nkv; ++j) {
+      const int valid = args.n_valid - j * kTileKV;  // columns >= valid are padding tokens
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+
+      // ---- pass 1: row max over the valid columns
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = __uint_as_float(r[i]);
+          mx = fmaxf(mx, (c * 32 + i < valid) ? s : -INFINITY);
+        }
+      }
+
+      // ---- reference-max update (lazy: only rescale O when the max grew by > 2^8)
+      bool waited_pv = false;
+      if (j == 0) {
+        m_ref = mx;
+      } else {
+        const float m_new = fmaxf(m_ref, mx);
+        const bool need = (m_new - m_ref) * sl2 > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(pv_done, (j - 1) & 1);  // O must be quiescent
+          waited_pv = true;
+          tc_fence_after();
+          const float alpha = need ? fast_exp2((m_ref - m_new) * sl2) : 1.f;
+          if (need) m_ref = m_new;
+          l *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_o + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st32(tmem_o + c * 32, r);
+          }
+          tmem_st_wait();
+        }
+      }
+      if (j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);  // P buffer free again
+
+      // ---- pass 2: P = exp2((s - m_ref) * sl2) -> bf16 -> swizzled smem; row sum
+      const float mb = m_ref * sl2;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + c * 32, r);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = __uint_as_float(r[i]);
+          const float e = fast_exp2(fmaf(s, sl2, -mb));
+          p[i] = (c * 32 + i < valid) ? e : 0.f;
+          l += p[i];
+        }
+        // 32 columns = 4 x 16-byte chunks of K-block (c >> 1), chunk index (c & 1) * 4 + q
+        uint8_t* blk = p_row + (c >> 1) * (kPBytes / 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c & 1) * 4 + q) ^ sw;
+          *reinterpret_cast<uint4*>(blk + chunk * 16) =
+              make_uint4(pack_bf16x2(p[8 * q + 0], p[8 * q + 1]), pack_bf16x2(p[8 * q + 2], p[8 * q + 3]),
+                         pack_bf16x2(p[8 * q + 4], p[8 * q + 5]), pack_bf16x2(p[8 * q + 6], p[8 * q + 7]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(s_free);        // S(j) fully read: QK^T(j+1) may overwrite it
+      fence_proxy_async_smem();   // P(j) visible to the tensor core (async proxy)
+      mbar_arrive(p_full);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> out[b, q, h*64 + d]
+    mbar_wait(pv_done, (nkv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const int b = bh / args.heads;
+    const int h = bh - b * args.heads;
+    const long long q_idx = static_cast<long long>(b) * args.npad + q_tile * kTileQ + row;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + q_idx * args.ldo + h * kDh;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_o + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[8 * q + i]) * inv_l;
+        st_global_v4(dst + c * 32 + 8 * q, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                     pack_bf16x2(f[6], f[7]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* vt, cudaStream_t stream) {
+  WVN_REQUIRE(a.batch > 0 && a.heads > 0, "attention: empty problem");
+  WVN_REQUIRE(a.npad % kTileKV == 0 && a.n_valid > 0 && a.n_valid <= a.npad && a.n_valid > a.npad - kTileKV,
+              "attention: npad=%d must be a multiple of 128 and n_valid=%d must lie in the last tile", a.npad,
+              a.n_valid);
+  const long long bh = static_cast<long long>(a.batch) * a.heads;
+  CUtensorMap tq, tk, tv;
+  WVN_PROPAGATE(make_tmap_bf16_2d(&tq, q, kDh, bh * a.npad, kDh * 2, 64, kTileQ));
+  WVN_PROPAGATE(make_tmap_bf16_2d(&tk, k, kDh, bh * a.npad, kDh * 2, 64, kTileKV));
+  WVN_PROPAGATE(make_tmap_bf16_2d(&tv, vt, a.npad, bh * kDh, static_cast<uint64_t>(a.npad) * 2, 64, kDh));
+  static bool attr_set = false;
+  if (!attr_set) {
+    WVN_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid(a.npad / kTileQ, static_cast<unsigned>(bh));
+  attention_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, a);
+  WVN_CHECK_LAUNCH("attention_kernel");
+  return WVN_OK;
+}
+
+}  // namespace wvn

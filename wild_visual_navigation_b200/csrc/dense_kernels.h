@@ -1,0 +1,34 @@
+// wvn-b200: internal interface of dense_kernels.cu (token grid <-> image resolution).
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace wvn {
+
+struct DenseArgs {
+  int batch = 0;
+  int dim = 0;                 // feature channels
+  int grid_h = 0, grid_w = 0;  // token grid
+  int out_h = 0, out_w = 0;    // output resolution
+  float scale_y = 0.f, scale_x = 0.f;  // (grid-1)/(out-1), align_corners=True
+  long long ld_out = 0;        // row pitch (elements) of interp_pixel_rows output
+};
+
+struct LogitsArgs {
+  int batch = 0;
+  int classes = 0;
+  int grid_h = 0, grid_w = 0;
+  int out_h = 0, out_w = 0;
+  float scale_y = 0.f, scale_x = 0.f;  // grid/out, align_corners=False
+  int npad = 0;                // rows per frame of the logits matrix (row 0 = CLS)
+  long long ld = 0;            // row pitch of the logits matrix
+  int col0 = 0;                // first logit column
+};
+
+// tokens: [B, grid_h*grid_w, dim] fp32 (CLS already dropped).
+int upsample_tokens_dense(const float* tokens, float* out_nchw, const DenseArgs& a, cudaStream_t stream);
+int interp_pixel_rows(const float* tokens, void* out_bf16, const DenseArgs& a, long long pix0, long long npix,
+                      cudaStream_t stream);
+int logits_argmax(const float* logits, long long* seg, const LogitsArgs& a, cudaStream_t stream);
+
+}  // namespace wvn

@@ -1,0 +1,166 @@
+// wvn-b200: memory-bound helper kernels of the ViT forward pass (sm_100a).
+//
+//   image_to_patches   : NEAREST resize + center crop + ImageNet normalisation + im2col -> bf16
+//                        (reference: dino_interface.py:52-59,81 transform, then the DINO
+//                         PatchEmbed Conv2d(3, D, p, p) expressed as a GEMM — SURVEY.md K1)
+//   init_token_rows    : CLS row (cls_token + pos_embed[0]) and zeroed padding rows
+//   layernorm_rows     : LayerNorm(D, eps) over the fp32 residual stream -> bf16 GEMM operand
+//                        (optionally also the fp32 patch-token output, CLS dropped — K2/K7)
+#include "common.cuh"
+#include "host_common.h"
+#include "vit_kernels.h"
+
+namespace wvn {
+
+namespace {
+
+// One thread produces 8 consecutive K-elements (one patch row of one channel for p=8):
+// reads 8 floats that are contiguous in the source row when no resize happens.
+__global__ void image_to_patches_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out,
+                                        ImagePatchArgs a) {
+  const int ps = a.patch;
+  const int k_total = 3 * ps * ps;
+  const int groups_per_row = k_total / 8;
+  const long long total = static_cast<long long>(a.batch) * a.grid_h * a.grid_w * groups_per_row;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups_per_row);
+    const long long prow = idx / groups_per_row;  // patch row index in [0, B*P)
+    const int pw = static_cast<int>(prow % a.grid_w);
+    const int ph = static_cast<int>((prow / a.grid_w) % a.grid_h);
+    const int b = static_cast<int>(prow / (static_cast<long long>(a.grid_w) * a.grid_h));
+    const int k0 = g * 8;  // k = c*ps*ps + ky*ps + kx
+    const int c = k0 / (ps * ps);
+    const int ky = (k0 / ps) % ps;
+    const int kx0 = k0 % ps;
+    // destination pixel in the cropped (size x size) image
+    const int y = ph * ps + ky;
+    // torch 'nearest': src = min(floor(dst * scale), in - 1), scale = in / out in fp32
+    const int sy = min(static_cast<int>(floorf((y + a.crop_top) * a.scale_y)), a.in_h - 1);
+    const float mean = a.mean[c], inv_std = a.inv_std[c];
+    const float* src_row = img + ((static_cast<long long>(b) * 3 + c) * a.in_h + sy) * a.in_w;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int x = pw * ps + kx0 + i;
+      const int sx = min(static_cast<int>(floorf((x + a.crop_left) * a.scale_x)), a.in_w - 1);
+      v[i] = (__ldg(src_row + sx) - mean) * inv_std;
+    }
+    st_global_v4(out + prow * k_total + k0, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                 pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+__global__ void init_token_rows_kernel(float* __restrict__ x, const float* __restrict__ cls,
+                                       const float* __restrict__ pos, int batch, int npad, int n_valid, int dim) {
+  // rows handled per frame: row 0 (CLS) and rows [n_valid, npad) (padding)
+  const int rows_per_frame = 1 + (npad - n_valid);
+  const long long total = static_cast<long long>(batch) * rows_per_frame * dim;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int d = static_cast<int>(idx % dim);
+    const long long r = idx / dim;
+    const int rr = static_cast<int>(r % rows_per_frame);
+    const int b = static_cast<int>(r / rows_per_frame);
+    const int row = (rr == 0) ? 0 : (n_valid + rr - 1);
+    x[(static_cast<long long>(b) * npad + row) * dim + d] = (rr == 0) ? (cls[d] + pos[d]) : 0.f;
+  }
+}
+
+// One warp per row, D = 128 * VEC_ITERS (384 -> 3, 768 -> 6).  Two-pass statistics in
+// registers (mean, then centred variance) — the same arithmetic order class as torch's LN.
+template <int ITERS>
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32, LayerNormArgs a) {
+  constexpr int D = 128 * ITERS;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp_global; row < a.rows; row += warps_total) {
+    const float4* src = reinterpret_cast<const float4*>(x + row * D);
+    float4 v[ITERS];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      v[i] = src[lane + 32 * i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + a.eps);
+    // optional fp32 output: only real patch tokens (CLS and padding dropped)
+    long long f32_row = -1;
+    if (out_f32 != nullptr) {
+      const int tok = static_cast<int>(row % a.npad);
+      const long long frame = row / a.npad;
+      if (tok >= 1 && tok < a.n_valid) f32_row = frame * (a.n_valid - 1) + (tok - 1);
+    }
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int c4 = lane + 32 * i;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + bt.x;
+      y.y = (v[i].y - mean) * rstd * g.y + bt.y;
+      y.z = (v[i].z - mean) * rstd * g.z + bt.z;
+      y.w = (v[i].w - mean) * rstd * g.w + bt.w;
+      if (out_bf16 != nullptr) {
+        uint2 p = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+        *reinterpret_cast<uint2*>(out_bf16 + row * D + 4 * c4) = p;
+      }
+      if (f32_row >= 0) reinterpret_cast<float4*>(out_f32 + f32_row * D)[c4] = y;
+    }
+  }
+}
+
+}  // namespace
+
+int image_to_patches(const float* img, void* out_bf16, const ImagePatchArgs& a, cudaStream_t stream) {
+  WVN_REQUIRE(a.patch == 8 || a.patch == 16, "image_to_patches: patch size %d unsupported", a.patch);
+  const long long total = static_cast<long long>(a.batch) * a.grid_h * a.grid_w * (3 * a.patch * a.patch / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long max_blocks = static_cast<long long>(sm_count()) * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  image_to_patches_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+      img, reinterpret_cast<__nv_bfloat16*>(out_bf16), a);
+  WVN_CHECK_LAUNCH("image_to_patches_kernel");
+  return WVN_OK;
+}
+
+int init_token_rows(float* x, const float* cls, const float* pos, int batch, int npad, int n_valid, int dim,
+                    cudaStream_t stream) {
+  const long long total = static_cast<long long>(batch) * (1 + npad - n_valid) * dim;
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 4096) blocks = 4096;
+  init_token_rows_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x, cls, pos, batch, npad, n_valid, dim);
+  WVN_CHECK_LAUNCH("init_token_rows_kernel");
+  return WVN_OK;
+}
+
+int layernorm_rows(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
+                   const LayerNormArgs& a, cudaStream_t stream) {
+  WVN_REQUIRE(a.dim == 384 || a.dim == 768, "layernorm: dim %d unsupported (384 or 768)", a.dim);
+  const int threads = 256;
+  long long blocks = (a.rows * 32 + threads - 1) / threads;
+  const long long max_blocks = static_cast<long long>(sm_count()) * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (a.dim == 384)
+    layernorm_rows_kernel<3><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, a);
+  else
+    layernorm_rows_kernel<6><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, a);
+  WVN_CHECK_LAUNCH("layernorm_rows_kernel");
+  return WVN_OK;
+}
+
+}  // namespace wvn

@@ -1,0 +1,33 @@
+// wvn-b200: internal interface of the memory-bound ViT helper kernels (vit_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace wvn {
+
+struct ImagePatchArgs {
+  int batch = 0;
+  int in_h = 0, in_w = 0;        // source image size
+  int patch = 8;
+  int grid_h = 0, grid_w = 0;    // patches per column / row of the cropped image
+  int crop_top = 0, crop_left = 0;  // center-crop offsets in the (virtually) resized image
+  float scale_y = 1.f, scale_x = 1.f;  // in / resized (torch 'nearest' source index scale)
+  float mean[3] = {0.485f, 0.456f, 0.406f};
+  float inv_std[3] = {1.f / 0.229f, 1.f / 0.224f, 1.f / 0.225f};
+};
+
+struct LayerNormArgs {
+  long long rows = 0;
+  int dim = 0;
+  float eps = 1e-6f;
+  // only used when an fp32 output is requested (drops CLS + padding rows)
+  int npad = 0, n_valid = 0;
+};
+
+int image_to_patches(const float* img, void* out_bf16, const ImagePatchArgs& a, cudaStream_t stream);
+int init_token_rows(float* x, const float* cls, const float* pos, int batch, int npad, int n_valid, int dim,
+                    cudaStream_t stream);
+int layernorm_rows(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
+                   const LayerNormArgs& a, cudaStream_t stream);
+
+}  // namespace wvn
