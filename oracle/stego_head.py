@@ -1,0 +1,82 @@
+"""ORACLE (test infrastructure only) — restatement of the STEGO segmentation head and probes.
+
+The arithmetic lives in the external ``stego`` package (``stego.stego.Stego``), absent from
+``/root/reference``; call sites: ``feature_extractor/stego_interface.py:43,91-100,107-109``.
+Restated from the public STEGO code [EXTERNAL-RECALLED, SURVEY.md §8 a4]:
+
+* ``segmentation_head``: ``cluster1 = Conv2d(C, dim, 1)``; ``cluster2 = Conv2d(C, C, 1) -> ReLU ->
+  Conv2d(C, dim, 1)``; ``code = cluster1(feats) + cluster2(feats)``   (dim = 90 in WVN)
+* ``get_code(img)``: ``(code(img) + code(img.flip(3)).flip(3)) / 2`` (horizontal-flip TTA)
+* ``postprocess``: ``code = F.interpolate(code, img.shape[-2:], 'bilinear', align_corners=False)``;
+  cluster probe = argmax_n <normalize(code), normalize(clusters_n)>; linear probe =
+  argmax(Conv2d(dim, n_classes, 1)(code)); CRF off (WVN default ``run_crf=False``).
+  Per-image k-means (``run_clustering=True``) is NOT restated.
+* ``StegoInterface.inference`` then upsamples code bilinear(align_corners=True) to (H, H) and the
+  predictions 'nearest' to (H, H) as int.
+
+PARITY STATUS: "parity unpinned" — no upstream weights or golden outputs exist in the reference.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+def synthetic_head(dim_in: int, code_dim: int = 90, n_clusters: int = 32, n_classes: int = 27, seed: int = 3) -> dict:
+    g = torch.Generator().manual_seed(seed)
+
+    def n(*shape, std):
+        return torch.randn(*shape, generator=g) * std
+
+    return {
+        "cluster1.0.weight": n(code_dim, dim_in, std=0.05),
+        "cluster1.0.bias": n(code_dim, std=0.05),
+        "cluster2.0.weight": n(dim_in, dim_in, std=0.05),
+        "cluster2.0.bias": n(dim_in, std=0.05),
+        "cluster2.2.weight": n(code_dim, dim_in, std=0.05),
+        "cluster2.2.bias": n(code_dim, std=0.05),
+        "cluster_probe.clusters": n(n_clusters, code_dim, std=1.0),
+        "linear_probe.weight": n(n_classes, code_dim, std=0.3),
+        "linear_probe.bias": n(n_classes, std=0.1),
+    }
+
+
+@torch.no_grad()
+def head_code(feats: torch.Tensor, hd: dict) -> torch.Tensor:
+    """feats: (B, C, h, w) -> code (B, dim, h, w)."""
+    def conv(x, w, b):
+        return F.conv2d(x, w[:, :, None, None], b)
+
+    c1 = conv(feats, hd["cluster1.0.weight"], hd["cluster1.0.bias"])
+    h = F.relu(conv(feats, hd["cluster2.0.weight"], hd["cluster2.0.bias"]))
+    c2 = conv(h, hd["cluster2.2.weight"], hd["cluster2.2.bias"])
+    return c1 + c2
+
+
+@torch.no_grad()
+def postprocess(code: torch.Tensor, out_hw: tuple[int, int], hd: dict):
+    """Returns (cluster_pred, linear_pred), each (B, H, W) long, computed the upstream way:
+    upsample the code first, then run the probes per pixel."""
+    code = F.interpolate(code, out_hw, mode="bilinear", align_corners=False)
+    normed_clusters = F.normalize(hd["cluster_probe.clusters"], dim=1)
+    normed_features = F.normalize(code, dim=1)
+    inner = torch.einsum("bchw,nc->bnhw", normed_features, normed_clusters)
+    cluster_pred = inner.argmax(1)
+    lin = F.conv2d(code, hd["linear_probe.weight"][:, :, None, None], hd["linear_probe.bias"])
+    linear_pred = lin.argmax(1)
+    return cluster_pred, linear_pred
+
+
+@torch.no_grad()
+def stego_inference(feats: torch.Tensor, feats_flipped: torch.Tensor | None, hd: dict, img_hw: tuple[int, int]):
+    """feats: backbone map of the transformed image; feats_flipped: backbone map of its horizontal
+    flip (None disables the flip TTA).  Returns (code_up (B,dim,H,H), cluster (B,H,H), linear (B,H,H))."""
+    code = head_code(feats, hd)
+    if feats_flipped is not None:
+        code = (code + head_code(feats_flipped, hd).flip(dims=[3])) / 2
+    H = img_hw[0]
+    cluster, linear = postprocess(code, img_hw, hd)
+    code_up = F.interpolate(code, (H, H), mode="bilinear", align_corners=True)
+    cluster = F.interpolate(cluster[None].float(), (H, H), mode="nearest").int()[0]
+    linear = F.interpolate(linear[None].float(), (H, H), mode="nearest").int()[0]
+    return code_up, cluster, linear

@@ -1,0 +1,227 @@
+"""ORACLE (test infrastructure only) — CPU/PyTorch fp32 restatement of the in-repo half of the
+WVN hot path.  Never imported by the product package.
+
+Each function cites the reference code it follows (paths relative to the reference repo).
+PARITY STATUS: pinned against the reference itself — ``tests/golden/make_golden.py`` path-imports
+the reference's own ``SimpleMLP`` / ``TraversabilityLoss`` / ``ConfidenceGenerator`` /
+``SegmentExtractor`` / ``DinoInterface.inference`` wrapper code from ``/root/reference`` and
+stores their outputs as fixtures; ``tests/test_oracle.py`` checks this file against them
+(plus the shipped known-answer ``assets/graph/{seg,center}.pt`` for the segment stage).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .dino_vit import ViTConfig, vit_feature_map
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+# ------------------------------------------------------------------------------------------
+# transform + DinoInterface.inference          (feature_extractor/dino_interface.py:52-59, 70-92)
+# ------------------------------------------------------------------------------------------
+def resized_size(in_h: int, in_w: int, size: int) -> tuple[int, int]:
+    """torchvision ``Resize(size:int)``: smaller edge -> size, aspect preserved (long = int(size*long/short))."""
+    if in_h <= in_w:
+        return size, int(size * in_w / in_h)
+    return int(size * in_h / in_w), size
+
+
+def wvn_transform(img: torch.Tensor, input_size: int) -> torch.Tensor:
+    """``T.Compose([Resize(input_size, NEAREST), CenterCrop(input_size), Normalize(...)])``."""
+    B, C, H, W = img.shape
+    rh, rw = resized_size(H, W, input_size)
+    if (rh, rw) != (H, W):
+        img = F.interpolate(img, size=(rh, rw), mode="nearest")
+    top = int(round((rh - input_size) / 2.0))
+    left = int(round((rw - input_size) / 2.0))
+    img = img[:, :, top : top + input_size, left : left + input_size]
+    mean = torch.tensor(IMAGENET_MEAN, dtype=img.dtype, device=img.device).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, dtype=img.dtype, device=img.device).view(1, 3, 1, 1)
+    return (img - mean) / std
+
+
+@torch.no_grad()
+def dino_inference(img: torch.Tensor, sd: dict, cfg: ViTConfig) -> torch.Tensor:
+    """``DinoInterface.inference``: transform -> backbone -> bilinear(align_corners=True) to (H, H).
+
+    Quirk kept: the output is (H, H) even if W != H (dino_interface.py:87-88)."""
+    feats = vit_feature_map(wvn_transform(img, cfg.image_size), sd, cfg)
+    H = img.shape[2]
+    return F.interpolate(feats, (H, H), mode="bilinear", align_corners=True)
+
+
+# ------------------------------------------------------------------------------------------
+# SegmentExtractor                              (feature_extractor/segment_extractor.py:40-92)
+# ------------------------------------------------------------------------------------------
+@torch.no_grad()
+def adjacency_list(seg: torch.Tensor) -> torch.Tensor:
+    """seg: (1,1,H,W) long.  Directed pairs (left/top id, right/bottom id) of 4-neighbour segment
+    boundaries, unique, ordered by key = left + right*(max+1) — what the reference's four shifted
+    difference filters + float64 ``torch.unique`` produce."""
+    s = seg[0, 0]
+    div = int(s.max()) + 1
+    hl, hr = s[:, :-1], s[:, 1:]
+    vt, vb = s[:-1, :], s[1:, :]
+    mh, mv = hl != hr, vt != vb
+    left = torch.cat([hl[mh], vt[mv]])
+    right = torch.cat([hr[mh], vb[mv]])
+    key = torch.unique(left + right * div)
+    return torch.stack([key % div, key // div], dim=1)
+
+
+@torch.no_grad()
+def centers(seg: torch.Tensor) -> torch.Tensor:
+    """Per-segment centroid in (x=col, y=row) order (segment_extractor.py:83-89)."""
+    s = seg[0, 0]
+    n = int(s.max()) + 1
+    out = []
+    for i in range(n):
+        ys, xs = torch.where(s == i)
+        out.append(torch.stack([xs.float().mean(), ys.float().mean()]))
+    return torch.stack(out)
+
+
+# ------------------------------------------------------------------------------------------
+# FeatureExtractor.sparsify_features default branch     (feature_extractor.py:389-396)
+# ------------------------------------------------------------------------------------------
+@torch.no_grad()
+def sparsify_features(dense: torch.Tensor, seg: torch.Tensor) -> torch.Tensor:
+    feats = []
+    for i in range(int(seg.max()) + 1):
+        x, y = torch.where(seg == i)
+        feats.append(dense[0, :, x, y].mean(dim=1))
+    return torch.stack(feats, dim=1).T
+
+
+def relabel(seg: torch.Tensor) -> torch.Tensor:
+    """``for i, k in enumerate(seg.unique()): seg[seg == k] = i`` (feature_extractor.py:245-246)."""
+    out = seg.clone()
+    for i, k in enumerate(seg.unique()):
+        out[seg == k] = i
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# SimpleMLP                                      (model/simple_mlp.py:10-39)
+# ------------------------------------------------------------------------------------------
+def mlp_init(dim: int = 384, hidden=(256, 32), seed: int = 42) -> dict:
+    """``torch.manual_seed(42); SimpleMLP(D, [256, 32, 1], reconstruction=True)`` — same module
+    construction order as the reference, so the same seeded init (traversability_estimator.py:78-80)."""
+    torch.manual_seed(seed)
+    sizes = list(hidden) + [1 + dim]
+    layers, inp = [], dim
+    for hs in sizes[:-1]:
+        layers.append(torch.nn.Linear(inp, hs))
+        layers.append(torch.nn.ReLU())
+        inp = hs
+    layers.append(torch.nn.Linear(inp, sizes[-1]))
+    seq = torch.nn.Sequential(*layers)
+    return {f"layers.{k}": v.detach().clone() for k, v in seq.state_dict().items()}
+
+
+def mlp_forward(x: torch.Tensor, sd: dict) -> torch.Tensor:
+    h = F.relu(F.linear(x, sd["layers.0.weight"], sd["layers.0.bias"]))
+    h = F.relu(F.linear(h, sd["layers.2.weight"], sd["layers.2.bias"]))
+    out = F.linear(h, sd["layers.4.weight"], sd["layers.4.bias"])
+    return torch.cat([torch.sigmoid(out[:, :1]), out[:, 1:]], dim=1)  # x[:, :1] = sigmoid(x[:, :1])
+
+
+# ------------------------------------------------------------------------------------------
+# ConfidenceGenerator                           (utils/confidence_generator.py:78-82, 182-193)
+# ------------------------------------------------------------------------------------------
+def confidence_inference(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, std_factor: float) -> torch.Tensor:
+    shifted = mean + std * std_factor
+    lo = torch.maximum(shifted - std, torch.zeros_like(std))
+    hi = shifted + std
+    xc = torch.clip(x, lo, hi)
+    return (1 - ((xc - lo) / (hi - lo))).float()
+
+
+# ------------------------------------------------------------------------------------------
+# TraversabilityLoss.forward                     (utils/loss.py:93-160), anomaly_balanced, MSE
+# ------------------------------------------------------------------------------------------
+def traversability_loss(res, x, y, y_valid, w_trav=0.03, w_reco=0.5, std_factor=0.5, anomaly_balanced=True):
+    """Returns (loss, aux) with aux holding loss_reco, loss_trav, loss_trav_confidence, confidence,
+    and the updated generator (mean, std) of method 'latest_measurement'."""
+    D = x.shape[1]
+    loss_reco = F.mse_loss(res[:, -D:], x, reduction="none").mean(dim=1)
+    with torch.no_grad():
+        pos = loss_reco[y_valid]
+        mean, std = pos.mean().reshape(1), pos.std().reshape(1)
+        conf = confidence_inference(loss_reco, mean, std, std_factor)
+    raw = F.mse_loss(res[:, :-D].squeeze(), y, reduction="none")
+    labeled = raw[y_valid]
+    unlabeled_w = raw[~y_valid] * (1 - conf)[~y_valid]
+    if anomaly_balanced:
+        l_trav = (unlabeled_w.sum() + labeled.sum()) / y.shape[0]
+    else:
+        l_trav = raw.mean()
+    l_reco = loss_reco[y_valid].mean()
+    loss = w_trav * l_trav + w_reco * l_reco
+    aux = {
+        "loss_reco": l_reco,
+        "loss_trav": raw.mean(),
+        "loss_trav_confidence": l_trav,
+        "confidence": conf,
+        "mean": mean,
+        "std": std,
+    }
+    return loss, aux
+
+
+def train_step(sd: dict, opt_state: dict, x, y, y_valid, lr=1e-3, **loss_kw):
+    """One ``TraversabilityEstimator.train()`` body (traversability_estimator.py:464-477) using
+    torch autograd + ``torch.optim.Adam`` on copies of ``sd``.  Returns (new_sd, new_opt_state, metrics)."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=lr)
+    if opt_state:
+        opt.load_state_dict(opt_state)
+    res = mlp_forward(x, params)
+    loss, aux = traversability_loss(res, x, y, y_valid, **loss_kw)
+    opt.zero_grad()
+    loss.backward()
+    grads = {k: v.grad.detach().clone() for k, v in params.items()}
+    opt.step()
+    new_sd = {k: v.detach().clone() for k, v in params.items()}
+    metrics = {
+        "loss_total": loss.item(),
+        "loss_trav": aux["loss_trav"].item(),
+        "loss_reco": aux["loss_reco"].item(),
+        "loss_trav_confidence": aux["loss_trav_confidence"].item(),
+        "mean": aux["mean"].item(),
+        "std": aux["std"].item(),
+        "confidence": aux["confidence"].detach(),
+        "grads": grads,
+    }
+    return new_sd, opt.state_dict(), metrics
+
+
+# ------------------------------------------------------------------------------------------
+# per-pixel inference          (wild_visual_navigation_ros/scripts/wvn_feature_extractor_node.py:319-370)
+# ------------------------------------------------------------------------------------------
+@torch.no_grad()
+def pixel_inference(dense: torch.Tensor, mlp_sd: dict, mean, std, std_factor: float):
+    """dense: (1, D, H, W) -> (trav (H,W), conf (H,W))."""
+    _, D, H, W = dense.shape
+    x = dense[0].permute(1, 2, 0).reshape(-1, D)
+    pred = mlp_forward(x, mlp_sd)
+    trav = pred.reshape(H, W, -1)[:, :, 0]
+    loss_reco = F.mse_loss(pred[:, 1:], x, reduction="none").mean(dim=1)
+    conf = confidence_inference(loss_reco, mean, std, std_factor).reshape(H, W)
+    return trav, conf
+
+
+def synthetic_supervision(n_rows: int, seed: int = 2, p_valid: float = 0.16):
+    """y_valid ~ Bernoulli(0.16), y = y_valid * U(0.001, 1] (mirrors assets/graph/graph.pt
+    statistics and the clamp(min=0.001) of supervision_generator.py:127)."""
+    g = torch.Generator().manual_seed(seed)
+    y_valid = torch.rand(n_rows, generator=g) < p_valid
+    if y_valid.sum() < 2:
+        y_valid[:2] = True
+    y = torch.where(y_valid, torch.rand(n_rows, generator=g).clamp(min=0.001), torch.zeros(n_rows))
+    return y, y_valid

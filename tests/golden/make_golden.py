@@ -1,0 +1,229 @@
+"""Generate the golden fixtures in tests/golden/ by running the REFERENCE's own code.
+
+Run in the build container (``/root/reference`` present):  ``python tests/golden/make_golden.py``
+
+The reference is pure Python; its torch-only modules are path-imported from the read-only tree
+(oracle/ref_import.py) and executed on seeded inputs.  The results are stored as small fixtures
+so that the GPU box (which has no ``/root/reference``) can still check the oracle — and through
+it the CUDA path — against what the reference computes.
+
+Fixtures
+  mlp_train.pt      reference SimpleMLP + TraversabilityLoss + torch.optim.Adam, 3 steps (small dims)
+  mlp_init_384.pt   checksum of the seed-42 init of the real-size SimpleMLP(384,[256,32,1],True)
+  confidence.pt     ConfidenceGenerator.inference_without_update / update (latest_measurement)
+  segments.npz      reference SegmentExtractor on a synthetic map + the reference's shipped
+                    known-answer assets/graph/{seg,center}.pt and graph.pt edge_index
+  dino_wrapper.pt   reference DinoInterface.inference (its real transform / upsample code) wrapped
+                    around the oracle's restated ViT (tiny config) via omegaconf/stego shims
+"""
+from __future__ import annotations
+
+import io
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import  # noqa: E402
+from oracle.dino_vit import ViTConfig, synthetic_state_dict, vit_feature_map  # noqa: E402
+
+
+def make_mlp_train(ns):
+    D, hidden = 32, [16, 8, 1]
+    torch.manual_seed(42)
+    model = ns.SimpleMLP(D, list(hidden), True)
+    init_sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    loss_fn = ns.TraversabilityLoss(
+        w_trav=0.03, w_reco=0.5, w_temp=0.0, anomaly_balanced=True, model=model, method="latest_measurement",
+        confidence_std_factor=0.5, log_enabled=False, log_folder="/tmp",
+    )
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    g = torch.Generator().manual_seed(7)
+    R = 96
+    x = torch.randn(R, D, generator=g)
+    y_valid = torch.rand(R, generator=g) < 0.25
+    y = torch.where(y_valid, torch.rand(R, generator=g).clamp(min=0.001), torch.zeros(R))
+    steps = []
+    for step in range(3):
+        graph = ns.Data(x=x, y=y, y_valid=y_valid)
+        res = model(graph)
+        loss, aux, _ = loss_fn(graph, res, step=step, log_step=False)
+        opt.zero_grad()
+        loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        opt.step()
+        steps.append(
+            {
+                "loss_total": loss.item(),
+                "loss_trav": aux["loss_trav"].item(),
+                "loss_reco": aux["loss_reco"].item(),
+                "loss_trav_confidence": aux["loss_trav_confidence"].item(),
+                "confidence": aux["confidence"].detach().clone(),
+                "cg_mean": loss_fn._confidence_generator.mean.detach().clone(),
+                "cg_std": loss_fn._confidence_generator.std.detach().clone(),
+                "grads": grads,
+                "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
+            }
+        )
+    # forward of the final model on fresh rows (inference semantics incl. in-place sigmoid)
+    xq = torch.randn(10, D, generator=g)
+    with torch.no_grad():
+        pred = model(ns.Data(x=xq.clone()))
+    torch.save(
+        {"dim": D, "hidden": hidden, "init_state_dict": init_sd, "x": x, "y": y, "y_valid": y_valid, "steps": steps,
+         "xq": xq, "pred": pred},
+        os.path.join(HERE, "mlp_train.pt"),
+    )
+
+
+def make_mlp_init(ns):
+    torch.manual_seed(42)
+    model = ns.SimpleMLP(384, [256, 32, 1], True)
+    sd = model.state_dict()
+    torch.save(
+        {"sums": {k: v.double().sum().item() for k, v in sd.items()},
+         "abs_sums": {k: v.double().abs().sum().item() for k, v in sd.items()},
+         "shapes": {k: tuple(v.shape) for k, v in sd.items()},
+         "first8": {k: v.flatten()[:8].clone() for k, v in sd.items()}},
+        os.path.join(HERE, "mlp_init_384.pt"),
+    )
+
+
+def make_confidence(ns):
+    cg = ns.ConfidenceGenerator(std_factor=0.5, method="latest_measurement")
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(200, generator=g) * 2.0
+    xp = x[:40]
+    with torch.no_grad():
+        conf_update = cg.update(x, xp, step=0)
+        mean, std = cg.mean.detach().clone(), cg.std.detach().clone()
+        conf_infer = cg.inference_without_update(x * 1.3)
+    # zero-interval-at-zero clamp case: mean small so that lo clamps to 0
+    cg2 = ns.ConfidenceGenerator(std_factor=1.0, method="latest_measurement")
+    with torch.no_grad():
+        cg2.mean[0], cg2.std[0] = 0.05, 0.2
+        conf_clamped = cg2.inference_without_update(x)
+    torch.save(
+        {"x": x, "x_positive": xp, "conf_update": conf_update, "mean": mean, "std": std, "conf_infer": conf_infer,
+         "conf_clamped": conf_clamped},
+        os.path.join(HERE, "confidence.pt"),
+    )
+
+
+def synthetic_segments(h=48, w=48, n=9, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    cy = torch.rand(n, generator=g) * h
+    cx = torch.rand(n, generator=g) * w
+    yy, xx = torch.meshgrid(torch.arange(h).float(), torch.arange(w).float(), indexing="ij")
+    d = (yy[None] - cy[:, None, None]) ** 2 + (xx[None] - cx[:, None, None]) ** 2
+    return d.argmin(0)
+
+
+def make_segments(ns):
+    se = ns.SegmentExtractor()
+    seg = synthetic_segments()[None, None]
+    edges = se.adjacency_list(seg)
+    cent = se.centers(seg)
+    out = {"syn_seg": seg[0, 0].numpy().astype(np.uint8), "syn_edges": edges.numpy(), "syn_centers": cent.numpy()}
+    # shipped known-answer fixture of the reference: assets/graph/{seg,center}.pt, graph.pt
+    adir = os.path.join(ns.root, "assets", "graph")
+    aseg = torch.load(os.path.join(adir, "seg.pt"), map_location="cpu")
+    acen = torch.load(os.path.join(adir, "center.pt"), map_location="cpu")
+    out["asset_seg"] = aseg.numpy().astype(np.uint8)
+    out["asset_centers"] = acen.numpy()
+    # graph.pt pickles a torch_geometric Data: unpickle with a stub class
+    tg = types.ModuleType("torch_geometric"); tgd = types.ModuleType("torch_geometric.data")
+    tgdd = types.ModuleType("torch_geometric.data.data"); tgds = types.ModuleType("torch_geometric.data.storage")
+
+    class _Any:
+        def __init__(self, *a, **k): pass
+        def __setstate__(self, st): self.__dict__.update(st if isinstance(st, dict) else {"state": st})
+
+    def _mod_getattr(name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Any
+
+    for m in (tgdd, tgds, tgd):
+        m.__getattr__ = _mod_getattr  # type: ignore
+    for name in ("Data", "DataEdgeAttr", "DataTensorAttr", "GlobalStorage"):
+        setattr(tgdd, name, type(name, (_Any,), {}))
+        setattr(tgds, name, type(name, (_Any,), {}))
+    sys.modules.update({"torch_geometric": tg, "torch_geometric.data": tgd, "torch_geometric.data.data": tgdd,
+                        "torch_geometric.data.storage": tgds})
+    try:
+        graph = torch.load(os.path.join(adir, "graph.pt"), map_location="cpu", weights_only=False)
+
+        def find(obj, key, depth=0):
+            if depth > 6: return None
+            d = getattr(obj, "__dict__", obj if isinstance(obj, dict) else None)
+            if not isinstance(d, dict): return None
+            if key in d and torch.is_tensor(d[key]): return d[key]
+            for v in d.values():
+                r = find(v, key, depth + 1)
+                if r is not None: return r
+            return None
+
+        ei = find(graph, "edge_index")
+        if ei is not None:
+            out["asset_edge_index"] = ei.numpy()
+    except Exception as e:  # pragma: no cover
+        print("graph.pt not decodable:", e)
+    finally:
+        for k in ("torch_geometric", "torch_geometric.data", "torch_geometric.data.data", "torch_geometric.data.storage"):
+            sys.modules.pop(k, None)
+    # reference outputs on its own asset (what the restatement must reproduce)
+    out["asset_ref_edges"] = se.adjacency_list(aseg[None, None]).numpy()
+    out["asset_ref_centers"] = se.centers(aseg[None, None]).numpy()
+    np.savez_compressed(os.path.join(HERE, "segments.npz"), **out)
+
+
+def make_dino_wrapper():
+    # shims for the two absent imports of dino_interface.py
+    class _Cfg(dict):
+        def is_empty(self): return len(self) == 0
+        __getattr__ = dict.__getitem__
+
+    om = types.ModuleType("omegaconf")
+    om.OmegaConf = types.SimpleNamespace(create=lambda d: _Cfg(d))
+    sys.modules["omegaconf"] = om
+    cfg = ViTConfig(image_size=32, patch_size=8, dim=32, depth=2, heads=2, mlp_dim=64, pretrain_grid=2)
+    sd = synthetic_state_dict(cfg, seed=21, attn_std=0.3)
+
+    class _Backbone(torch.nn.Module):
+        def forward(self, x): return vit_feature_map(x, sd, cfg)
+
+    st = types.ModuleType("stego"); stb = types.ModuleType("stego.backbones"); stbb = types.ModuleType("stego.backbones.backbone")
+    stbb.get_backbone = lambda c: _Backbone()
+    sys.modules.update({"stego": st, "stego.backbones": stb, "stego.backbones.backbone": stbb})
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_dino_interface", os.path.join(ref_import.REF_ROOT, "wild_visual_navigation/feature_extractor/dino_interface.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    di = mod.DinoInterface(device="cpu", backbone="dino", input_size=32, backbone_type="vit_small", patch_size=8)
+    g = torch.Generator().manual_seed(9)
+    img = torch.rand(1, 3, 40, 52, generator=g)
+    out = di.inference(img.clone())
+    img2 = torch.rand(2, 3, 32, 32, generator=g)
+    out2 = di.inference(img2.clone())
+    torch.save({"vit_seed": 21, "attn_std": 0.3, "cfg": cfg.__dict__, "img": img, "out": out, "img2": img2, "out2": out2},
+               os.path.join(HERE, "dino_wrapper.pt"))
+
+
+if __name__ == "__main__":
+    assert ref_import.available(), "needs /root/reference"
+    ns = ref_import.load()
+    make_mlp_train(ns)
+    make_mlp_init(ns)
+    make_confidence(ns)
+    make_segments(ns)
+    make_dino_wrapper()
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,88 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/wvn_b200.h declares, the package imports without a GPU, and the host-side containers
+behave like the reference's."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    import __graft_entry__ as g
+
+    if not os.path.exists(os.path.join(ROOT, "wild_visual_navigation_b200", "libwvn_b200.so")):
+        g.build()
+    from wild_visual_navigation_b200 import _C
+
+    return _C
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "wvn_b200.h")).read()
+    declared = set(re.findall(r"\b(wvn_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 28
+    l = built_lib.lib()
+    for name in declared:
+        assert hasattr(l, name), f"libwvn_b200.so lacks {name}"
+    assert declared == set(built_lib.SIGNATURES), declared ^ set(built_lib.SIGNATURES)
+    assert l.wvn_version() >= 100
+
+
+def test_no_gpu_means_loud_failure(built_lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert built_lib.lib().wvn_check_device() == -3
+    with pytest.raises(built_lib.WvnError):
+        built_lib.require_device()
+    from wild_visual_navigation_b200 import DinoInterface
+
+    with pytest.raises(Exception):
+        DinoInterface("cpu")
+
+
+def test_data_batch_semantics():
+    from wild_visual_navigation_b200 import Batch, Data
+
+    d1 = Data(x=torch.zeros(3, 4), y=torch.ones(3), y_valid=torch.tensor([True, False, True]),
+              edge_index=torch.tensor([[0, 1], [1, 2]]))
+    d2 = Data(x=torch.ones(2, 4), y=torch.zeros(2), y_valid=torch.tensor([False, False]),
+              edge_index=torch.tensor([[0], [1]]))
+    b = Batch.from_data_list([d1, d2])
+    assert b.x.shape == (5, 4) and b.y.shape == (5,) and b.ba == 5
+    assert b.ptr.tolist() == [0, 3, 5] and b.batch.tolist() == [0, 0, 0, 1, 1]
+    assert b.edge_index.tolist() == [[0, 1, 3], [1, 2, 4]]
+    assert Batch.from_data_list([]) is None
+
+
+def test_simple_mlp_state_dict_layout_and_quirk():
+    from wild_visual_navigation_b200 import SimpleMLP, get_model
+
+    hs = [256, 32, 1]
+    m = SimpleMLP(384, hs, True)
+    assert hs == [256, 32, 385]  # the reference mutates the caller's list (simple_mlp.py:21-22)
+    assert m.nr_sigmoid_layers == 1 and m.output_features == 385
+    sd = m.state_dict()
+    assert [tuple(v.shape) for v in sd.values()] == [(256, 384), (256,), (32, 256), (32,), (385, 32), (385,)]
+    assert m.flat_params.numel() == 119489
+    # parameters are views into the flat buffer, and load_state_dict writes through
+    new = {k: torch.full_like(v, 0.5) for k, v in sd.items()}
+    m.load_state_dict(new)
+    assert torch.all(m.flat_params == 0.5)
+    m2 = get_model({"name": "SimpleMLP", "simple_mlp_cfg": {"input_size": 90, "hidden_sizes": [256, 32, 1], "reconstruction": True}})
+    assert m2.output_features == 91
+
+
+def test_confidence_generator_state_dict_keys():
+    from wild_visual_navigation_b200 import ConfidenceGenerator, TraversabilityLoss, SimpleMLP
+
+    cg = ConfidenceGenerator(0.5, "latest_measurement")
+    assert set(cg.state_dict()) == {"mean", "var", "std"}
+    assert cg.var.shape == (1, 1)
+    loss = TraversabilityLoss(0.03, 0.5, 0.0, True, SimpleMLP(8, [4, 2, 1], True), "latest_measurement", 0.5)
+    assert set(loss.state_dict()) == {"_confidence_generator.mean", "_confidence_generator.var", "_confidence_generator.std"}
+    x = torch.rand(10)
+    assert torch.equal(cg.inference_without_update(x.to("meta")) if False else cg.inference_without_update(x), cg.inference_without_update(x))

@@ -1,0 +1,145 @@
+"""FeatureExtractor (reference: wild_visual_navigation/feature_extractor/feature_extractor.py:20-398).
+
+``extract(img, **kwargs) -> (edges, feat, seg, center, dense_feat)`` with the reference's kwargs
+(``return_dense_features``, ``n_random_pixels``, ``cell_size``).  Differences in HOW, not WHAT:
+  * the per-segment mean of the bilinearly upsampled features is computed from the ViT tokens by a
+    segmented reduction (csrc/segment_kernels.cu) — the 308 MB/frame dense tensor is formed only
+    when ``return_dense_features=True`` asks for it;
+  * adjacency + centroids come from the same pass (no per-segment Python loops / host syncs);
+  * when segmentation and features are both "stego"/"dino" on the same backbone, one ViT forward
+    serves both (the reference runs two backbones).
+Supported on the hot path: segmentation_type in {"stego", "grid", "random", "none"/None},
+feature_type in {"dino", "stego"}.  "slic" (fast_slic), "sift", "torchvision", "histogram" are
+out of scope and raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from .dino_interface import DinoInterface
+from .segment_extractor import SegmentExtractor
+from .stego_interface import StegoInterface
+
+
+class FeatureExtractor:
+    def __init__(self, device: str, segmentation_type: str = "slic", feature_type: str = "dino",
+                 input_size: int = 448, **kwargs):
+        self._device = device
+        self._segmentation_type = segmentation_type
+        self._feature_type = feature_type
+        self._input_size = input_size
+        self.segment_extractor = SegmentExtractor()
+        if segmentation_type not in ("stego", "grid", "random", "none", None):
+            raise ValueError(f"segmentation_type [{segmentation_type}] is outside the B200 hot path")
+        common = dict(backbone_type=kwargs.get("backbone_type", "vit_small"), patch_size=kwargs.get("patch_size", 8),
+                      max_batch=kwargs.get("max_batch", 1), chunk=kwargs.get("chunk", 0))
+        need_stego = feature_type == "stego" or segmentation_type == "stego"
+        if feature_type == "stego":
+            self._feature_dim = 90
+        elif "dino" in feature_type:
+            # the reference hard-codes 384 for every dino variant (feature_extractor.py:56)
+            self._feature_dim = 384 if common["backbone_type"] == "vit_small" else 768
+        else:
+            raise ValueError(f"Extractor[{feature_type}] is outside the B200 hot path")
+        if need_stego:
+            self._stego = StegoInterface(device=device, input_size=input_size, run_crf=kwargs.get("run_crf", False),
+                                         run_clustering=kwargs.get("run_clustering", False),
+                                         n_image_clusters=kwargs.get("n_image_clusters", 20),
+                                         head_state_dict=kwargs.get("head_state_dict"),
+                                         backbone_state_dict=kwargs.get("state_dict"),
+                                         flip_tta=kwargs.get("flip_tta", True), **common)
+            self._dino = self._stego._dino
+            self._extractor = self._stego if feature_type == "stego" else self._dino
+        else:
+            self._stego = None
+            self._dino = DinoInterface(device=device, input_size=input_size, backbone=kwargs.get("backbone", "dino"),
+                                       state_dict=kwargs.get("state_dict"),
+                                       pretrained_weights=kwargs.get("pretrained_weights"), **common)
+            self._extractor = self._dino
+
+    # ---- reference properties ---------------------------------------------------------------
+    @property
+    def feature_type(self):
+        return self._feature_type
+
+    @property
+    def feature_dim(self):
+        return self._feature_dim
+
+    @property
+    def segmentation_type(self):
+        return self._segmentation_type
+
+    def change_device(self, device):
+        self._device = device
+        self._extractor.change_device(device)
+
+    # ---- the hot call -----------------------------------------------------------------------
+    @torch.no_grad()
+    def extract(self, img, **kwargs):
+        img = img.to(self._device, dtype=torch.float32)
+        B, _, H, W = img.shape
+        assert B == 1, "extract() keeps the reference's single-frame contract; use extract_batch() for B > 1"
+        r = self.extract_batch(img, **kwargs)
+        n = int(r["n_segments"][0].item())
+        seg = r["seg"][0]
+        feat = r["feat"][0, :n]
+        dense = r["dense"] if kwargs.get("return_dense_features", False) else None
+        if self._segmentation_type == "random":
+            return None, feat, seg, None, dense
+        ne = int(r["n_edges"][0].item())
+        edges = r["edges"][0, :ne].T.contiguous()
+        center = r["centers"][0, :n]
+        return edges, feat, seg, center, dense
+
+    @torch.no_grad()
+    def extract_batch(self, img, **kwargs):
+        """Batched form of ``extract`` (no per-frame host sync): returns padded device tensors
+        seg [B,H,W] i64, feat [B,smax,D], centers [B,smax,2], edges [B,E,2], n_edges [B], n_segments [B]."""
+        img = img.to(self._device, dtype=torch.float32)
+        B, _, H, W = img.shape
+        g = self._dino.grid
+        # 1. segmentation (+ the one backbone pass)
+        tokens = None
+        if self._segmentation_type == "stego":
+            self._stego.inference(img)
+            seg = self._stego.cluster_segments[0].long().contiguous()
+            counts = ops.relabel(seg, self._stego._n_clusters)
+            smax = self._stego._n_clusters
+            tokens = self._stego.code_tokens if self._feature_type == "stego" else self._stego.backbone_tokens
+        elif self._segmentation_type == "grid":
+            cell = kwargs.get("cell_size", 32)
+            ys = torch.arange(H, device=img.device) // cell
+            xs = torch.arange(W, device=img.device) // cell
+            ncol = (W + cell - 1) // cell
+            seg = (ys[:, None] * ncol + xs[None, :]).expand(B, H, W).contiguous()
+            smax = int(((H + cell - 1) // cell) * ncol)
+            counts = torch.full((B,), smax, device=img.device, dtype=torch.int32)
+        elif self._segmentation_type == "random":
+            nr = kwargs.get("n_random_pixels", 100)
+            seg = torch.full((B, H * W), -1, dtype=torch.long, device=img.device)
+            for b in range(B):
+                idx = torch.randperm(H * W, device=img.device)[:nr]
+                seg[b, idx] = torch.arange(0, nr, device=img.device)
+            seg = seg.reshape(B, H, W)
+            smax = nr
+            counts = torch.full((B,), nr, device=img.device, dtype=torch.int32)
+        else:  # pixel-wise ("none"): every pixel is its own segment — dense features are the features
+            raise ValueError("segmentation_type 'none' returns dense features; call DinoInterface.inference "
+                             "or TraversabilityInference (per-pixel path) instead")
+        # 2. features
+        if tokens is None:
+            if self._feature_type == "stego":
+                self._stego.inference(img)
+                tokens = self._stego.code_tokens
+            else:
+                tokens = self._dino.inference_tokens(img)
+        # 3. per-segment pooling + graph structure in one pass
+        want_graph = self._segmentation_type != "random"
+        r = ops.segment_reduce(seg, smax, tokens=tokens, grid=(g, g), want_centers=want_graph, want_edges=want_graph)
+        out = {"seg": seg, "feat": r["feat"], "centers": r["centers"], "edges": r["edges"], "n_edges": r["n_edges"],
+               "n_segments": counts, "tokens": tokens, "dense": None}
+        if kwargs.get("return_dense_features", False):
+            out["dense"] = ops.upsample_dense(tokens, g, g, H, H)
+        return out

@@ -1,0 +1,126 @@
+"""StegoInterface (reference: wild_visual_navigation/feature_extractor/stego_interface.py:19-135).
+
+``inference(img) -> (linear_pred, cluster_pred)`` with the ``features`` / ``cluster_segments`` /
+``linear_segments`` properties.  The STEGO head runs as three tcgen05 GEMMs on the ViT tokens
+(csrc/api.cu: wvn_vit_stego_head); the cluster / linear probes are folded into the head's output
+columns (weights.fold_stego_head) and evaluated at patch resolution, then one kernel does the
+bilinear(align_corners=False) upsampling + argmax per pixel — algebraically the upstream
+``postprocess`` (upsample the 90-d code, then probe every pixel) without the 448x448x90 tensor.
+CRF and per-image k-means are not on the hot path (``run_crf`` / ``run_clustering`` must be False).
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from .dino_interface import DinoInterface, _Cfg
+from .weights import (HEAD_CLUSTER_COL, HEAD_CODE_COL, HEAD_LINEAR_COL, fold_stego_head, synthetic_stego_head)
+
+
+class StegoInterface:
+    def __init__(self, device: str, input_size: int = 448, model_path: str = None, n_image_clusters: int = 40,
+                 run_crf: bool = False, run_clustering: bool = False, cfg=None, backbone_type: str = "vit_small",
+                 patch_size: int = 8, head_state_dict=None, backbone_state_dict=None, flip_tta: bool = True,
+                 max_batch: int = 32, chunk: int = 0, code_dim: int = 90):
+        self._cfg = _Cfg(cfg) if cfg else _Cfg(model_path=model_path, input_size=input_size, run_crf=run_crf,
+                                               run_clustering=run_clustering, n_image_clusters=n_image_clusters)
+        if self._cfg.run_crf or self._cfg.run_clustering:
+            raise ValueError("run_crf / run_clustering (CRF, per-image k-means) are outside the B200 hot path "
+                             "(SURVEY.md §8f rank 4); construct with both False")
+        self._device = device
+        self._flip_tta = flip_tta
+        if head_state_dict is None:
+            if model_path:
+                ck = torch.load(model_path, map_location="cpu")
+                sd = ck.get("state_dict", ck)
+                head_state_dict = {k.replace("segmentation_head.", ""): v.squeeze(-1).squeeze(-1) if v.dim() == 4 else v
+                                   for k, v in sd.items() if k.startswith(("segmentation_head.", "cluster_probe.",
+                                                                           "linear_probe."))}
+                head_state_dict = {k.replace("cluster_probe.clusters", "cluster_probe.clusters"): v
+                                   for k, v in head_state_dict.items()}
+                if backbone_state_dict is None:
+                    backbone_state_dict = {k.split("backbone.model.", 1)[1]: v for k, v in sd.items()
+                                           if "backbone.model." in k} or None
+            else:
+                from .weights import VIT_SHAPES
+                head_state_dict = synthetic_stego_head(VIT_SHAPES[backbone_type]["dim"], code_dim)
+        self._head = head_state_dict
+        self._code_dim = int(head_state_dict["cluster1.0.weight"].shape[0])
+        self._n_clusters = int(head_state_dict["cluster_probe.clusters"].shape[0])
+        self._n_classes = int(head_state_dict["linear_probe.weight"].shape[0])
+        self._dino = DinoInterface(device, input_size=input_size, backbone_type=backbone_type, patch_size=patch_size,
+                                   max_batch=max_batch * (2 if flip_tta else 1), chunk=chunk,
+                                   state_dict=backbone_state_dict, head_weights=fold_stego_head(head_state_dict))
+        self._code = self._cluster_pred = self._linear_pred = None
+        self._tokens = None
+
+    def change_device(self, device):
+        self._dino.change_device(device)
+
+    @torch.no_grad()
+    def inference(self, img: torch.Tensor):
+        """img (B,3,H,W) -> (linear_pred, cluster_pred), each (1,B,H,H) int32 like the reference."""
+        img = img.to(self._device, dtype=torch.float32)
+        B, _, H, W = img.shape
+        vit = self._dino._model
+        g, npad = vit.grid, vit.npad
+        if self._flip_tta:
+            # Stego.get_code: average with the horizontally flipped pass (flip back at patch level)
+            both = torch.cat([img, img.flip(dims=[3])], dim=0)
+            tokens = vit.forward(both)
+            out = vit.stego_head(2 * B).view(2, B, npad, -1)
+            a = out[0, :, 1 : 1 + g * g].reshape(B, g, g, -1)
+            b = out[1, :, 1 : 1 + g * g].reshape(B, g, g, -1).flip(dims=[2])
+            head = torch.zeros(B, npad, out.shape[-1], device=img.device)
+            head[:, 1 : 1 + g * g] = ((a + b) * 0.5).reshape(B, g * g, -1)
+            head = head.view(B * npad, -1)
+            self._tokens = tokens[:B]
+        else:
+            self._tokens = vit.forward(img)
+            head = vit.stego_head(B)
+        S = self._cfg.input_size
+        cl = ops.logits_argmax(head, HEAD_CLUSTER_COL, self._n_clusters, B, npad, g, g, S, S)
+        li = ops.logits_argmax(head, HEAD_LINEAR_COL, self._n_classes, B, npad, g, g, S, S)
+        code = head.view(B, npad, -1)[:, 1 : 1 + g * g, HEAD_CODE_COL : HEAD_CODE_COL + self._code_dim].contiguous()
+        self._code_tokens = code  # (B, P, 90) at patch resolution — what the fused consumers use
+        self._code = None         # dense (B,90,H,H) only on demand (property `features`)
+        self._img_hw = (H, W)
+        if (S, S) != (H, H):
+            cl = torch.nn.functional.interpolate(cl[None].float(), (H, H), mode="nearest")[0].long()
+            li = torch.nn.functional.interpolate(li[None].float(), (H, H), mode="nearest")[0].long()
+        self._cluster_pred = cl[None].int()
+        self._linear_pred = li[None].int()
+        return self._linear_pred, self._cluster_pred
+
+    @property
+    def model(self):
+        return self._dino._model
+
+    @property
+    def input_size(self):
+        return self._cfg.input_size
+
+    @property
+    def linear_segments(self):
+        return self._linear_pred
+
+    @property
+    def cluster_segments(self):
+        return self._cluster_pred
+
+    @property
+    def code_tokens(self):
+        return self._code_tokens
+
+    @property
+    def backbone_tokens(self):
+        return self._tokens
+
+    @property
+    def features(self):
+        """Dense (B, 90, H, H) code, bilinear align_corners=True (stego_interface.py:107) — materialised lazily."""
+        if self._code is None:
+            g = self._dino.grid
+            H = self._img_hw[0]
+            self._code = ops.upsample_dense(self._code_tokens, g, g, H, H)
+        return self._code

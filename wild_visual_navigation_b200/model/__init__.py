@@ -1,0 +1,2 @@
+from .simple_mlp import SimpleMLP
+from .network_register import get_model

@@ -1,0 +1,308 @@
+"""Tensor-level wrappers over the C ABI (include/wvn_b200.h).
+
+Everything here is plumbing: allocate outputs with torch, pass raw pointers + the current stream
+to libwvn_b200.so.  The classes in ``feature_extractor/``, ``model/``, ``utils/`` and
+``traversability_estimator/`` (the reference's API surface) are built on these.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from ctypes import byref, c_void_p
+
+import torch
+import torch.nn.functional as F
+
+from . import _C
+from ._C import TrainConfig, VitConfig, check, lib, ptr, stream
+
+OUT_BF16, OUT_F32, OUT_RESID_F32 = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+
+
+# --------------------------------------------------------------------------------------------
+# primitives
+# --------------------------------------------------------------------------------------------
+def gemm_bf16(a, w, bias=None, out_kind=OUT_BF16, act=ACT_NONE, out=None, block_n=0):
+    """out = act(a @ w.T + bias).  a: [M,K] bf16, w: [N,K] bf16, bias: [N] f32."""
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16 if out_kind == OUT_BF16 else torch.float32)
+    check(lib().wvn_gemm_bf16(ptr(a), a.stride(0), ptr(w), ptr(bias), ptr(out), out.stride(0), M, N, K, out_kind, act,
+                              block_n, stream()))
+    return out
+
+
+def attention(q, k, vt, n_valid, scale=0.125):
+    """q,k: [B,H,npad,64] bf16; vt: [B,H,64,npad] bf16 -> [B,npad,H*64] bf16."""
+    B, H, npad, dh = q.shape
+    assert dh == 64
+    out = torch.empty(B, npad, H * 64, device=q.device, dtype=torch.bfloat16)
+    check(lib().wvn_attention_bf16(ptr(q), ptr(k), ptr(vt), ptr(out), B, H, npad, n_valid, scale, stream()))
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-6):
+    rows, dim = x.shape
+    out = torch.empty(rows, dim, device=x.device, dtype=torch.bfloat16)
+    check(lib().wvn_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), rows, dim, eps, stream()))
+    return out
+
+
+def upsample_dense(tokens, gh, gw, out_h, out_w):
+    """tokens [B, gh*gw, D] f32 -> (B, D, out_h, out_w) f32, bilinear align_corners=True."""
+    B, P, D = tokens.shape
+    out = torch.empty(B, D, out_h, out_w, device=tokens.device, dtype=torch.float32)
+    check(lib().wvn_upsample_dense(ptr(tokens), ptr(out), B, D, gh, gw, out_h, out_w, stream()))
+    return out
+
+
+def logits_argmax(logits, col0, classes, batch, npad, gh, gw, out_h, out_w):
+    seg = torch.empty(batch, out_h, out_w, device=logits.device, dtype=torch.int64)
+    check(lib().wvn_logits_argmax(ptr(logits), logits.stride(0), col0, classes, batch, npad, gh, gw, out_h, out_w,
+                                  ptr(seg), stream()))
+    return seg
+
+
+def segment_reduce(seg, smax, tokens=None, grid=None, want_centers=True, want_edges=True, max_edges=None):
+    """seg: [B,H,W] int64.  Returns dict(feat [B,smax,D] | None, centers [B,smax,2] | None,
+    edges [B,max_edges,2] | None, n_edges [B] int32 | None)."""
+    B, H, W = seg.shape
+    dev = seg.device
+    if tokens is not None:
+        gh, gw = grid
+        D = tokens.shape[-1]
+    else:
+        gh = gw = 1
+        D = 0
+    ws_bytes = lib().wvn_segment_workspace_bytes(B, smax, gh, gw)
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    feat = torch.empty(B, smax, D, device=dev, dtype=torch.float32) if tokens is not None else None
+    centers = torch.empty(B, smax, 2, device=dev, dtype=torch.float32) if want_centers else None
+    if want_edges:
+        if max_edges is None:
+            max_edges = min(smax * smax, 8 * smax + 64)
+        edges = torch.zeros(B, max_edges, 2, device=dev, dtype=torch.int64)
+        n_edges = torch.zeros(B, device=dev, dtype=torch.int32)
+    else:
+        max_edges, edges, n_edges = 0, None, None
+    check(lib().wvn_segment_reduce(ptr(seg), B, H, W, smax, ptr(tokens), gh, gw, D, ptr(feat), ptr(centers), ptr(edges),
+                                   ptr(n_edges), max_edges, ptr(ws), stream()))
+    return {"feat": feat, "centers": centers, "edges": edges, "n_edges": n_edges, "max_edges": max_edges}
+
+
+def relabel(seg, num_labels):
+    """In-place relabel of each frame of seg [B,H,W] to 0..S-1; returns counts [B] int32."""
+    B = seg.shape[0]
+    scratch = torch.empty(B * num_labels, device=seg.device, dtype=torch.int32)
+    counts = torch.empty(B, device=seg.device, dtype=torch.int32)
+    check(lib().wvn_segment_relabel(ptr(seg), B, seg[0].numel(), num_labels, ptr(scratch), ptr(counts), stream()))
+    return counts
+
+
+# --------------------------------------------------------------------------------------------
+# ViT backbone handle
+# --------------------------------------------------------------------------------------------
+def interpolate_pos_embed(pos_embed: torch.Tensor, grid: int) -> torch.Tensor:
+    """DINO's interpolate_pos_encoding (bicubic, +0.1 trick), done once at weight-load time."""
+    n_pre = pos_embed.shape[1] - 1
+    if n_pre == grid * grid:
+        return pos_embed
+    dim = pos_embed.shape[-1]
+    side = int(math.sqrt(n_pre))
+    w0 = h0 = grid + 0.1
+    patch = F.interpolate(pos_embed[:, 1:].reshape(1, side, side, dim).permute(0, 3, 1, 2).float(),
+                          scale_factor=(h0 / side, w0 / side), mode="bicubic")
+    patch = patch.permute(0, 2, 3, 1).reshape(1, -1, dim)
+    return torch.cat((pos_embed[:, :1], patch), dim=1)
+
+
+class ViTBackbone:
+    """Owns a ``wvn_vit_t``: DINO ViT weights (bf16 on device) + L2-sized activation workspaces."""
+
+    def __init__(self, image_size, patch_size, dim, depth, heads, mlp_dim, state_dict, max_batch=32, chunk=0,
+                 head_weights=None, ln_eps=1e-6):
+        _C.require_device()
+        self.image_size, self.patch_size, self.dim = image_size, patch_size, dim
+        self.grid = image_size // patch_size
+        self.P = self.grid * self.grid
+        self.max_batch = max_batch
+        self.head_out = 0 if head_weights is None else int(head_weights["head_a.weight"].shape[0])
+        cfg = VitConfig(image_size, patch_size, dim, depth, heads, mlp_dim, max_batch, chunk, ln_eps, self.head_out)
+        h = c_void_p()
+        check(lib().wvn_vit_create(byref(cfg), byref(h)))
+        self._h = h
+        self.npad = lib().wvn_vit_npad(h)
+        self._load(state_dict, depth)
+        if head_weights is not None:
+            for k, v in head_weights.items():
+                self._set("stego." + k, v)
+
+    def _set(self, name, t):
+        t = t.detach().to(dtype=torch.float32, device="cpu").contiguous()
+        check(lib().wvn_vit_set_weight(self._h, name.encode(), c_void_p(t.data_ptr()), t.numel()))
+
+    def _load(self, sd, depth):
+        sd = {k.replace("module.", "").replace("backbone.", ""): v for k, v in sd.items()}
+        self._set("cls_token", sd["cls_token"].reshape(-1))
+        self._set("pos_embed", interpolate_pos_embed(sd["pos_embed"].float().cpu(), self.grid).reshape(-1))
+        self._set("patch_embed.proj.weight", sd["patch_embed.proj.weight"].reshape(self.dim, -1))
+        self._set("patch_embed.proj.bias", sd["patch_embed.proj.bias"])
+        for i in range(depth):
+            for leaf in ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight",
+                         "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias",
+                         "mlp.fc2.weight", "mlp.fc2.bias"):
+                self._set(f"blocks.{i}.{leaf}", sd[f"blocks.{i}.{leaf}"])
+        self._set("norm.weight", sd["norm.weight"])
+        self._set("norm.bias", sd["norm.bias"])
+
+    def forward(self, img: torch.Tensor, resized_hw=None) -> torch.Tensor:
+        """img: (B,3,H,W) f32 CUDA in [0,1] -> final-norm patch tokens (B, P, D) f32."""
+        B, C, H, W = img.shape
+        assert C == 3 and img.dtype == torch.float32
+        img = img.contiguous()
+        if resized_hw is None:
+            resized_hw = _resized_size(H, W, self.image_size)
+        tokens = torch.empty(B, self.P, self.dim, device=img.device, dtype=torch.float32)
+        check(lib().wvn_vit_forward(self._h, ptr(img), B, H, W, resized_hw[0], resized_hw[1], ptr(tokens), stream()))
+        return tokens
+
+    def stego_head(self, batch: int) -> torch.Tensor:
+        out = torch.empty(batch * self.npad, self.head_out, device="cuda", dtype=torch.float32)
+        check(lib().wvn_vit_stego_head(self._h, batch, ptr(out), stream()))
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().wvn_vit_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def _resized_size(h, w, size):
+    # torchvision Resize(size:int): smaller edge -> size
+    if h <= w:
+        return size, int(size * w / h)
+    return int(size * h / w), size
+
+
+# --------------------------------------------------------------------------------------------
+# traversability MLP: inference handle and trainer
+# --------------------------------------------------------------------------------------------
+class MlpInference:
+    def __init__(self, dim=384, h1=256, h2=32, chunk_rows=0):
+        _C.require_device()
+        self.dim, self.h1, self.h2 = dim, h1, h2
+        h = c_void_p()
+        check(lib().wvn_mlp_infer_create(dim, h1, h2, chunk_rows, byref(h)))
+        self._h = h
+
+    def set_params(self, flat_params: torch.Tensor):
+        assert flat_params.is_cuda and flat_params.dtype == torch.float32
+        check(lib().wvn_mlp_infer_set_params(self._h, ptr(flat_params.contiguous()), stream()))
+
+    def pixels(self, tokens, grid, out_hw, cg_mean, cg_std, std_factor):
+        B = tokens.shape[0]
+        trav = torch.empty(B, out_hw[0], out_hw[1], device=tokens.device, dtype=torch.float32)
+        conf = torch.empty_like(trav)
+        check(lib().wvn_mlp_infer_pixels(self._h, ptr(tokens), B, grid[0], grid[1], out_hw[0], out_hw[1], ptr(cg_mean),
+                                         ptr(cg_std), float(std_factor), ptr(trav), ptr(conf), stream()))
+        return trav, conf
+
+    def rows(self, x, cg_mean, cg_std, std_factor):
+        R = x.shape[0]
+        trav = torch.empty(R, device=x.device, dtype=torch.float32)
+        conf = torch.empty_like(trav)
+        check(lib().wvn_mlp_infer_rows(self._h, ptr(x.contiguous()), R, ptr(cg_mean), ptr(cg_std), float(std_factor),
+                                       ptr(trav), ptr(conf), stream()))
+        return trav, conf
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().wvn_mlp_infer_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def mlp_forward_f32(flat_params, x, dim, h1, h2):
+    """SimpleMLP.forward in fp32: returns (rows, 1+dim) with column 0 through the sigmoid."""
+    R = x.shape[0]
+    dev = x.device
+    b1 = torch.empty(R, h1, device=dev, dtype=torch.float32)
+    b2 = torch.empty(R, h2, device=dev, dtype=torch.float32)
+    out = torch.empty(R, 1 + dim, device=dev, dtype=torch.float32)
+    check(lib().wvn_mlp_forward_f32(dim, h1, h2, ptr(flat_params), ptr(x.contiguous()), R, ptr(b1), ptr(b2), ptr(out),
+                                    stream()))
+    return out
+
+
+class MlpTrainer:
+    """Fused online train step on a flat fp32 parameter buffer (see csrc/mlp_train.cu).
+
+    ``params`` is the tensor that SimpleMLP's layers view into, so the reference's state_dict
+    layout stays intact.  With ``process_group`` set, the confidence statistics and the flat
+    gradient are summed across ranks (one all-reduce each) for an exact global-batch step."""
+
+    def __init__(self, params, dim=384, h1=256, h2=32, max_rows=4096, w_trav=0.03, w_reco=0.5, std_factor=0.5,
+                 anomaly_balanced=True, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+        _C.require_device()
+        self.dim, self.h1, self.h2, self.max_rows = dim, h1, h2, max_rows
+        self.n_params = lib().wvn_mlp_param_count(dim, h1, h2)
+        assert params.numel() == self.n_params and params.is_cuda and params.dtype == torch.float32
+        dev = params.device
+        self.params = params
+        self.grads = torch.zeros(self.n_params + 1, device=dev)
+        self.exp_avg = torch.zeros(self.n_params, device=dev)
+        self.exp_avg_sq = torch.zeros(self.n_params, device=dev)
+        self.step_counter = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.cfg = TrainConfig(w_trav, w_reco, std_factor, int(anomaly_balanced), lr, betas[0], betas[1], eps)
+        self.scalars = torch.zeros(lib().wvn_mlp_train_scalars_bytes() // 8, device=dev, dtype=torch.float64)
+        self.metrics = torch.zeros(6, device=dev)
+        self.cg_mean = torch.zeros(1, device=dev)
+        self.cg_std = torch.ones(1, device=dev)
+        self.pg = process_group
+        self._alloc_ws(max_rows)
+
+    def _alloc_ws(self, max_rows):
+        self.max_rows = max_rows
+        nbytes = lib().wvn_mlp_train_workspace_bytes(self.dim, self.h1, self.h2, max_rows)
+        self.ws = torch.empty(nbytes // 4, device=self.params.device, dtype=torch.float32)
+        self.conf = torch.empty(max_rows, device=self.params.device, dtype=torch.float32)
+
+    def step(self, x, y, y_valid, n_total=None):
+        """x [R,D] f32, y [R] f32, y_valid [R] bool.  Returns the confidence vector [R]; metrics stay
+        on the device in ``self.metrics`` (loss_total, loss_trav, loss_reco, loss_trav_conf, mean, std)."""
+        R = x.shape[0]
+        if R > self.max_rows:
+            self._alloc_ws(int(R * 1.5))
+        x = x.contiguous()
+        y = y.contiguous().float()
+        yv = y_valid.contiguous().to(torch.uint8)
+        d = (self.dim, self.h1, self.h2)
+        s = stream()
+        check(lib().wvn_mlp_train_forward_stats(*d, ptr(self.params), ptr(x), ptr(y), ptr(yv), R, self.max_rows,
+                                                ptr(self.ws), ptr(self.scalars), s))
+        if self.pg is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.scalars[:5], group=self.pg)
+            if n_total is None:
+                nt = torch.tensor([R], device=x.device, dtype=torch.int64)
+                dist.all_reduce(nt, group=self.pg)
+                n_total = int(nt.item())
+        if n_total is None:
+            n_total = R
+        check(lib().wvn_mlp_train_backward(*d, ptr(self.params), ptr(x), ptr(y), ptr(yv), R, self.max_rows, n_total,
+                                           byref(self.cfg), ptr(self.ws), ptr(self.scalars), ptr(self.cg_mean),
+                                           ptr(self.cg_std), ptr(self.grads), ptr(self.conf), s))
+        if self.pg is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, group=self.pg)
+        check(lib().wvn_mlp_train_apply(*d, ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                        ptr(self.step_counter), n_total, byref(self.cfg), ptr(self.scalars), s))
+        check(lib().wvn_mlp_train_read_metrics(ptr(self.scalars), ptr(self.metrics), s))
+        return self.conf[:R]

@@ -1,0 +1,3 @@
+from .data import Data, Batch
+from .confidence_generator import ConfidenceGenerator
+from .loss import TraversabilityLoss
