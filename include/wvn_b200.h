@@ -44,6 +44,13 @@ const char* wvn_last_error(void);
 /* 0 if device 0..n has compute capability 10.x, WVN_STATUS_NO_DEVICE otherwise. */
 int wvn_check_device(void);
 int wvn_version(void);
+/* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */
+long long wvn_launch_count(void);
+/* Optional CUDA-event timing of the dominant kernels inside real steps (bench.py roofline):
+ * category 0 = fused attention, 1 = tcgen05 GEMMs.  collect() synchronises and writes the summed
+ * milliseconds / launch counts per category into HOST arrays of length 2 and clears the records. */
+void wvn_profile_enable(int on);
+int wvn_profile_collect(float* host_ms, long long* host_launches);
 
 /* ------------------------------------------------------------------------------------------
  * Primitive: bf16 tensor-core GEMM  C = A[M,K] * W[N,K]^T  (tcgen05, fp32 accumulate)

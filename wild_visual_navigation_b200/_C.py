@@ -42,6 +42,9 @@ SIGNATURES = {
     "wvn_last_error": (c_char_p, []),
     "wvn_check_device": (_I, []),
     "wvn_version": (_I, []),
+    "wvn_launch_count": (_L, []),
+    "wvn_profile_enable": (None, [_I]),
+    "wvn_profile_collect": (_I, [_P, _P]),
     "wvn_gemm_bf16": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
     "wvn_attention_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "wvn_layernorm": (_I, [_P, _P, _P, _P, _L, _I, _F, _P]),

@@ -115,6 +115,13 @@ int wvn_check_device(void) {
   return WVN_OK;
 }
 
+long long wvn_launch_count(void) { return launch_count(); }
+void wvn_profile_enable(int on) { prof_enable(on != 0); }
+int wvn_profile_collect(float* host_ms, long long* host_launches) {
+  WVN_REQUIRE(host_ms && host_launches, "wvn_profile_collect: null argument");
+  return prof_collect(host_ms, host_launches);
+}
+
 // -------------------------------------------------------------------------------- primitives
 int wvn_gemm_bf16(const void* a, long long lda, const void* w, const float* bias, void* out, long long ldo, int m, int n,
                   int k, int out_kind, int act, int block_n, void* stream) {

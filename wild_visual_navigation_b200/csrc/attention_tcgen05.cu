@@ -302,7 +302,9 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
     attr_set = true;
   }
   dim3 grid(a.npad / kTileQ, static_cast<unsigned>(bh));
+  prof_begin(PROF_ATTENTION, stream);
   attention_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, a);
+  prof_end(PROF_ATTENTION, stream);
   WVN_CHECK_LAUNCH("attention_kernel");
   return WVN_OK;
 }

@@ -325,7 +325,9 @@ int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
   int grid = sm_count();
   if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
   if (grid > num_tiles) grid = num_tiles;
+  prof_begin(PROF_GEMM, stream);
   kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, a);
+  prof_end(PROF_GEMM, stream);
   WVN_CHECK_LAUNCH("gemm_bf16_kernel");
   return WVN_OK;
 }

@@ -5,6 +5,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 namespace wvn {
 
 static thread_local char g_err[512] = "";
@@ -63,6 +67,63 @@ int sm_count() {
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   return n;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(); }
+
+namespace {
+struct ProfRec { int cat; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_pool;
+cudaEvent_t g_open[PROF_NUM] = {nullptr, nullptr};
+cudaEvent_t get_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+void prof_enable(bool on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on;
+}
+
+void prof_begin(int cat, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on) return;
+  g_open[cat] = get_event();
+  cudaEventRecord(g_open[cat], s);
+}
+
+void prof_end(int cat, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on || g_open[cat] == nullptr) return;
+  cudaEvent_t b = get_event();
+  cudaEventRecord(b, s);
+  g_prof.push_back({cat, g_open[cat], b});
+  g_open[cat] = nullptr;
+}
+
+int prof_collect(float* ms_by_cat, long long* launches_by_cat) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < PROF_NUM; ++i) { ms_by_cat[i] = 0.f; launches_by_cat[i] = 0; }
+  for (auto& r : g_prof) {
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e != cudaSuccess) return set_error(WVN_ERR_CUDA, "profiler: %s", cudaGetErrorString(e));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    ms_by_cat[r.cat] += ms;
+    launches_by_cat[r.cat] += 1;
+    g_pool.push_back(r.a);
+    g_pool.push_back(r.b);
+  }
+  g_prof.clear();
+  return WVN_OK;
 }
 
 }  // namespace wvn

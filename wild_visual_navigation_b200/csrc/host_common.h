@@ -30,6 +30,7 @@ const char* last_error();
 
 #define WVN_CHECK_LAUNCH(name)                                                                        \
   do {                                                                                                \
+    ::wvn::count_launch();                                                                            \
     cudaError_t _e = cudaGetLastError();                                                              \
     if (_e != cudaSuccess)                                                                            \
       return ::wvn::set_error(::wvn::WVN_ERR_CUDA, "launch of %s failed: %s (%s:%d)", name,           \
@@ -53,5 +54,16 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t inner, uint64
                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
 int sm_count();
+
+// Kernel-launch counter (every launch of one of this library's kernels) and an optional
+// CUDA-event profiler used by bench.py to time the dominant kernels inside a real step.
+void count_launch();
+long long launch_count();
+enum ProfCategory : int { PROF_ATTENTION = 0, PROF_GEMM = 1, PROF_NUM = 2 };
+void prof_enable(bool on);
+void prof_begin(int cat, cudaStream_t s);
+void prof_end(int cat, cudaStream_t s);
+// Synchronises, sums elapsed ms per category, clears the record list.
+int prof_collect(float* ms_by_cat, long long* launches_by_cat);
 
 }  // namespace wvn
