@@ -16,6 +16,8 @@
 //   warp 1    : MMA issuer  (S = Q K^T : 4 x UMMA 128x128x16;  O += P V : 8 x UMMA 128x64x16)
 //   warps 2-5 : softmax (1 thread = 1 query row): tcgen05.ld S, online softmax with lazy
 //               rescaling, P -> bf16 -> swizzled smem, final O / l epilogue.
+#include <stdlib.h>
+
 #include "attention.h"
 #include "common.cuh"
 #include "host_common.h"
@@ -43,6 +45,7 @@ constexpr uint32_t kTmemCols = 256;  // S: [0,128)  O: [128,192)
 constexpr uint32_t kColS = 0;
 constexpr uint32_t kColO = 128;
 constexpr float kRescaleThreshold = 8.0f;  // in log2 units (FA4-style lazy rescale)
+constexpr int kDefaultPoly = 0;            // software-exp2 share: pairs out of every 4 pairs (see poly_exp2_pair)
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -50,6 +53,56 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// ---- packed fp32x2 helpers (sm_100: FFMA2 / FADD2 / FMNMX3 halve the issue slots of the softmax) ----
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// exp2 on the FMA/ALU pipes (Cody-Waite + degree-3 minimax, rel. err 7.5e-5 — well inside the bf16
+// rounding of P): the MUFU unit (16 ex2/clk/SM) is the binding resource of the softmax phase, so
+// POLY of every 4 element PAIRS are evaluated here instead (FA4-style software exp2 offload).
+__device__ __forceinline__ void poly_exp2_pair(uint64_t x2, float& e0, float& e1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x2 = pack2(fmaxf(x0, -120.f), fmaxf(x1, -120.f));      // keep the exponent arithmetic in range
+  const uint64_t t2 = add2(x2, pack2(12582912.f, 12582912.f));     // 1.5*2^23: low mantissa bits = round(x)
+  const uint64_t n2 = add2(t2, pack2(-12582912.f, -12582912.f));
+  const uint64_t f2 = fma2(n2, pack2(-1.f, -1.f), x2);             // f = x - round(x) in [-0.5, 0.5]
+  uint64_t p2 = fma2(f2, pack2(0.0551716685f, 0.0551716685f), pack2(0.2426111251f, 0.2426111251f));
+  p2 = fma2(p2, f2, pack2(0.6932609677f, 0.6932609677f));
+  p2 = fma2(p2, f2, pack2(0.9999280572f, 0.9999280572f));
+  float p0, p1, t0, t1;
+  unpack2(p2, p0, p1);
+  unpack2(t2, t0, t1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));   // p * 2^round(x)
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
+__device__ __forceinline__ float masked_exp(float s, float sl2, float mb, int col, int valid) {
+  return (col < valid) ? fast_exp2(fmaf(s, sl2, -mb)) : 0.f;
+}
+
+template <int POLY>
 __global__ void __launch_bounds__(kThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_vt, const AttnArgs args) {
@@ -180,16 +233,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tc_fence_after();
 
       // ---- pass 1: row max over the valid columns
+      const bool masked = valid < kTileKV;  // only the last KV tile carries padding keys
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_s + c * 32, r);
         tmem_ld_wait();
+        if (!masked) {
+          float m0 = -INFINITY, m1 = -INFINITY;  // two FMNMX3 chains
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(r[i]);
-          mx = fmaxf(mx, (c * 32 + i < valid) ? s : -INFINITY);
+          for (int i = 0; i < 32; i += 4) {
+            m0 = max3(m0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+            m1 = max3(m1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+          }
+          const float m2 = -INFINITY, m3 = -INFINITY;
+          mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float s = __uint_as_float(r[i]);
+            mx = fmaxf(mx, (c * 32 + i < valid) ? s : -INFINITY);
+          }
         }
       }
 
@@ -229,12 +294,31 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tmem_ld32(tmem_s + c * 32, r);
         tmem_ld_wait();
         float p[32];
+        if (!masked) {
+          const uint64_t sl2_2 = pack2(sl2, sl2), nmb2 = pack2(-mb, -mb);
+          uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(r[i]);
-          const float e = fast_exp2(fmaf(s, sl2, -mb));
-          p[i] = (c * 32 + i < valid) ? e : 0.f;
-          l += p[i];
+          for (int i = 0; i < 32; i += 2) {
+            const uint64_t x2 = fma2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sl2_2, nmb2);
+            if (((i >> 1) & 3) < POLY) {
+              poly_exp2_pair(x2, p[i], p[i + 1]);
+            } else {
+              float x0, x1;
+              unpack2(x2, x0, x1);
+              p[i] = fast_exp2(x0);
+              p[i + 1] = fast_exp2(x1);
+            }
+            if ((i >> 1) & 1) lb = add2(lb, pack2(p[i], p[i + 1])); else la = add2(la, pack2(p[i], p[i + 1]));
+          }
+          float s0, s1;
+          unpack2(add2(la, lb), s0, s1);
+          l += s0 + s1;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            p[i] = masked_exp(__uint_as_float(r[i]), sl2, mb, c * 32 + i, valid);
+            l += p[i];
+          }
         }
         // 32 columns = 4 x 16-byte chunks of K-block (c >> 1), chunk index (c & 1) * 4 + q
         uint8_t* blk = p_row + (c >> 1) * (kPBytes / 2);
@@ -296,15 +380,27 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
   WVN_PROPAGATE(make_tmap_bf16_2d(&tq, q, kDh, bh * a.npad, kDh * 2, 64, kTileQ));
   WVN_PROPAGATE(make_tmap_bf16_2d(&tk, k, kDh, bh * a.npad, kDh * 2, 64, kTileKV));
   WVN_PROPAGATE(make_tmap_bf16_2d(&tv, vt, a.npad, bh * kDh, static_cast<uint64_t>(a.npad) * 2, 64, kDh));
-  static bool attr_set = false;
-  if (!attr_set) {
-    WVN_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
+  // fraction (in quarters) of the exponentials evaluated on the FMA pipe; tuned on B200, overridable
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("WVN_ATTN_POLY");
+    poly = e ? atoi(e) : kDefaultPoly;
+    if (poly < 0 || poly > 3) poly = kDefaultPoly;
   }
   dim3 grid(a.npad / kTileQ, static_cast<unsigned>(bh));
-  prof_begin(PROF_ATTENTION, stream);
-  attention_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, a);
-  prof_end(PROF_ATTENTION, stream);
+  auto launch = [&](auto kern) -> int {
+    WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    prof_begin(PROF_ATTENTION, stream);
+    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, a);
+    prof_end(PROF_ATTENTION, stream);
+    return WVN_OK;
+  };
+  switch (poly) {
+    case 0: WVN_PROPAGATE(launch(attention_kernel<0>)); break;
+    case 1: WVN_PROPAGATE(launch(attention_kernel<1>)); break;
+    case 2: WVN_PROPAGATE(launch(attention_kernel<2>)); break;
+    default: WVN_PROPAGATE(launch(attention_kernel<3>)); break;
+  }
   WVN_CHECK_LAUNCH("attention_kernel");
   return WVN_OK;
 }

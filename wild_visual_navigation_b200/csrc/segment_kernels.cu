@@ -12,6 +12,8 @@
 //   feat[s] = (sum_p W[s,p] * tok[p]) / count[s],   W[s,p] = sum_{pixels in s} bilinear weight of patch p,
 // so one pass over the pixels accumulates W (plus counts, coordinate sums and adjacency bits)
 // and a small second kernel contracts W with the token grid.
+#include <algorithm>
+
 #include "common.cuh"
 #include "host_common.h"
 #include "segment_kernels.h"
@@ -72,49 +74,149 @@ segment_accumulate_kernel(const long long* __restrict__ seg, SegmentArgs a, unsi
   }
 }
 
-// grid (smax, B), 128 threads; contracts the (sparse) weight row with the token grid.
-__global__ void __launch_bounds__(128)
-segment_pool_kernel(const float* __restrict__ wseg, const float* __restrict__ tok,
-                    const unsigned long long* __restrict__ stats, float* __restrict__ feat,
-                    float* __restrict__ centers, SegmentArgs a) {
-  __shared__ float w_sm[128];
-  const int s = blockIdx.x;
-  const long long b = blockIdx.y;
+// ---- privatised accumulation -----------------------------------------------------------------
+// One block = one TILE_H x TILE_W pixel tile of one frame.  The tile touches only a small window
+// of the token grid, so the bilinear weights W[s, token], the per-segment statistics and the
+// adjacency bits are first accumulated in shared memory (cheap, contention-free across SMs) and
+// only the non-zero entries are flushed with global atomics.  Used when smax <= kPrivMaxSeg.
+constexpr int kTileH = 8, kTileW = 64, kPrivMaxSeg = 128;
+
+__global__ void __launch_bounds__(256)
+segment_accumulate_tiled_kernel(const long long* __restrict__ seg, SegmentArgs a, int win_h, int win_w,
+                                unsigned long long* __restrict__ stats, float* __restrict__ wseg,
+                                unsigned int* __restrict__ adj) {
+  extern __shared__ float sm_w[];                               // [smax][win_h][win_w]
+  int* sm_stats = reinterpret_cast<int*>(sm_w + a.smax * win_h * win_w);  // [smax][3]
+  unsigned int* sm_adj = reinterpret_cast<unsigned int*>(sm_stats + a.smax * 3);  // [smax][words]
+  const int adj_words = (a.smax + 31) >> 5;
   const int P = a.grid_h * a.grid_w;
-  const unsigned long long* st = stats + (b * a.smax + s) * 3;
-  const float cnt = static_cast<float>(st[0]);
-  if (threadIdx.x == 0 && centers != nullptr) {
-    // torch: nonzero(...).float().mean(0) -> (mean col, mean row); empty segment -> NaN
-    centers[(b * a.smax + s) * 2 + 0] = static_cast<float>(static_cast<double>(st[1]) / static_cast<double>(st[0]));
-    centers[(b * a.smax + s) * 2 + 1] = static_cast<float>(static_cast<double>(st[2]) / static_cast<double>(st[0]));
-  }
-  if (feat == nullptr) return;
-  const float* wrow = wseg + (b * a.smax + s) * P;
-  const float* tb = tok + b * P * a.dim;
-  constexpr int kMaxPer = 8;  // dim <= 1024
-  float acc[kMaxPer];
-#pragma unroll
-  for (int i = 0; i < kMaxPer; ++i) acc[i] = 0.f;
-  for (int p0 = 0; p0 < P; p0 += 128) {
-    __syncthreads();
-    w_sm[threadIdx.x] = (p0 + threadIdx.x < P) ? wrow[p0 + threadIdx.x] : 0.f;
-    __syncthreads();
-    const int lim = min(128, P - p0);
-    for (int q = 0; q < lim; ++q) {
-      const float w = w_sm[q];
-      if (w == 0.f) continue;  // block-uniform branch
-      const float* tr = tb + static_cast<long long>(p0 + q) * a.dim;
-#pragma unroll
-      for (int i = 0; i < kMaxPer; ++i) {
-        const int c = threadIdx.x + 128 * i;
-        if (c < a.dim) acc[i] = fmaf(w, __ldg(tr + c), acc[i]);
+  const long long b = blockIdx.z;
+  const int px0 = blockIdx.x * kTileW, py0 = blockIdx.y * kTileH;
+  const int n_w = a.smax * win_h * win_w;
+  for (int i = threadIdx.x; i < n_w; i += blockDim.x) sm_w[i] = 0.f;
+  for (int i = threadIdx.x; i < a.smax * 3; i += blockDim.x) sm_stats[i] = 0;
+  for (int i = threadIdx.x; i < a.smax * adj_words; i += blockDim.x) sm_adj[i] = 0u;
+  // token window origin of this tile
+  int wy0, wx0, t1;
+  float tw;
+  ac_true_coord(py0, a.scale_y, a.grid_h, wy0, t1, tw);
+  ac_true_coord(px0, a.scale_x, a.grid_w, wx0, t1, tw);
+  __syncthreads();
+  const long long* segb = seg + b * a.h * a.w;
+  for (int i = threadIdx.x; i < kTileH * kTileW; i += blockDim.x) {
+    const int x = px0 + (i % kTileW), y = py0 + (i / kTileW);
+    if (x >= a.w || y >= a.h) continue;
+    const long long s = segb[static_cast<long long>(y) * a.w + x];
+    if (s < 0 || s >= a.smax) continue;
+    atomicAdd(&sm_stats[s * 3 + 0], 1);
+    atomicAdd(&sm_stats[s * 3 + 1], x);
+    atomicAdd(&sm_stats[s * 3 + 2], y);
+    if (wseg != nullptr) {
+      int x0, x1, y0, y1;
+      float wx, wy;
+      ac_true_coord(x, a.scale_x, a.grid_w, x0, x1, wx);
+      ac_true_coord(y, a.scale_y, a.grid_h, y0, y1, wy);
+      float* w = sm_w + s * win_h * win_w;
+      atomicAdd(w + (y0 - wy0) * win_w + (x0 - wx0), (1.f - wy) * (1.f - wx));
+      atomicAdd(w + (y0 - wy0) * win_w + (x1 - wx0), (1.f - wy) * wx);
+      atomicAdd(w + (y1 - wy0) * win_w + (x0 - wx0), wy * (1.f - wx));
+      atomicAdd(w + (y1 - wy0) * win_w + (x1 - wx0), wy * wx);
+    }
+    if (adj != nullptr) {
+      if (x + 1 < a.w) {
+        const long long r = segb[static_cast<long long>(y) * a.w + x + 1];
+        if (r != s && r >= 0 && r < a.smax) atomicOr(&sm_adj[r * adj_words + (s >> 5)], 1u << (s & 31));
+      }
+      if (y + 1 < a.h) {
+        const long long r = segb[static_cast<long long>(y + 1) * a.w + x];
+        if (r != s && r >= 0 && r < a.smax) atomicOr(&sm_adj[r * adj_words + (s >> 5)], 1u << (s & 31));
       }
     }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.smax; i += blockDim.x) {
+    if (sm_stats[i * 3] != 0) {
+      unsigned long long* st = stats + (b * a.smax + i) * 3;
+      atomicAdd(st + 0, static_cast<unsigned long long>(sm_stats[i * 3 + 0]));
+      atomicAdd(st + 1, static_cast<unsigned long long>(sm_stats[i * 3 + 1]));
+      atomicAdd(st + 2, static_cast<unsigned long long>(sm_stats[i * 3 + 2]));
+    }
+  }
+  if (wseg != nullptr) {
+    for (int i = threadIdx.x; i < n_w; i += blockDim.x) {
+      const float v = sm_w[i];
+      if (v != 0.f) {
+        const int s = i / (win_h * win_w), r = (i / win_w) % win_h, c = i % win_w;
+        const int ty = wy0 + r, tx = wx0 + c;
+        if (ty < a.grid_h && tx < a.grid_w) atomicAdd(wseg + (b * a.smax + s) * P + ty * a.grid_w + tx, v);
+      }
+    }
+  }
+  if (adj != nullptr) {
+    for (int i = threadIdx.x; i < a.smax * adj_words; i += blockDim.x)
+      if (sm_adj[i] != 0u) atomicOr(adj + b * a.smax * adj_words + i, sm_adj[i]);
+  }
+}
+
+// feat_sum[b][s][d] += sum_p W[b][s][p] * tok[b][p][d]   (small dense GEMM; W is segments x tokens)
+// grid (ceil(dim/64), ceil(smax/32), B * ksplit); 256 threads: thread -> column tx, 8 rows.
+__global__ void __launch_bounds__(256)
+segment_pool_gemm_kernel(const float* __restrict__ wseg, const float* __restrict__ tok, float* __restrict__ feat,
+                         SegmentArgs a, int ksplit) {
+  __shared__ float Ws[32][33];
+  __shared__ float Ts[32][64];
+  const int P = a.grid_h * a.grid_w;
+  const long long b = blockIdx.z / ksplit;
+  const int split = blockIdx.z % ksplit;
+  const int kper = ((P + ksplit - 1) / ksplit + 31) / 32 * 32;
+  const int k_beg = split * kper, k_end = min(P, k_beg + kper);
+  const int c0 = blockIdx.x * 64, s0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 63, ry = threadIdx.x >> 6;  // rows ry*8 .. ry*8+7
+  float acc[8];
 #pragma unroll
-  for (int i = 0; i < kMaxPer; ++i) {
-    const int c = threadIdx.x + 128 * i;
-    if (c < a.dim) feat[(b * a.smax + s) * a.dim + c] = acc[i] / cnt;
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const float* wb = wseg + (b * a.smax) * P;
+  const float* tb = tok + b * P * a.dim;
+  for (int k0 = k_beg; k0 < k_end; k0 += 32) {
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+      const int r = i >> 5, k = i & 31;
+      Ws[r][k] = (s0 + r < a.smax && k0 + k < k_end) ? wb[static_cast<long long>(s0 + r) * P + k0 + k] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+      const int k = i >> 6, c = i & 63;
+      Ts[k][c] = (k0 + k < k_end && c0 + c < a.dim) ? tb[static_cast<long long>(k0 + k) * a.dim + c0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float t = Ts[k][tx];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(Ws[ry * 8 + i][k], t, acc[i]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int s = s0 + ry * 8 + i;
+    if (s < a.smax && c0 + tx < a.dim && acc[i] != 0.f) atomicAdd(&feat[(b * a.smax + s) * a.dim + c0 + tx], acc[i]);
+  }
+}
+
+// feat = feat_sum / count; centers = (mean col, mean row).  Empty segment -> NaN, like torch's mean of empty.
+__global__ void __launch_bounds__(256)
+segment_finalize_kernel(const unsigned long long* __restrict__ stats, float* __restrict__ feat,
+                        float* __restrict__ centers, SegmentArgs a) {
+  const long long n_seg = static_cast<long long>(a.batch) * a.smax;
+  const long long total = feat ? n_seg * a.dim : n_seg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long sidx = feat ? i / a.dim : i;
+    const unsigned long long* st = stats + sidx * 3;
+    if (feat) feat[i] = feat[i] / static_cast<float>(st[0]);
+    if (centers && (!feat || i % a.dim == 0)) {
+      centers[sidx * 2 + 0] = static_cast<float>(static_cast<double>(st[1]) / static_cast<double>(st[0]));
+      centers[sidx * 2 + 1] = static_cast<float>(static_cast<double>(st[2]) / static_cast<double>(st[0]));
+    }
   }
 }
 
@@ -203,6 +305,24 @@ int segment_accumulate(const long long* seg, const SegmentArgs& a, unsigned long
   WVN_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * 3 * a.batch * a.smax, stream));
   if (wseg) WVN_CHECK_CUDA(cudaMemsetAsync(wseg, 0, sizeof(float) * a.batch * a.smax * P, stream));
   if (adj) WVN_CHECK_CUDA(cudaMemsetAsync(adj, 0, sizeof(unsigned int) * a.batch * a.smax * ((a.smax + 31) >> 5), stream));
+  if (a.smax <= kPrivMaxSeg) {
+    const int win_h = static_cast<int>((kTileH - 1) * a.scale_y) + 3;
+    const int win_w = static_cast<int>((kTileW - 1) * a.scale_x) + 3;
+    const size_t smem = sizeof(float) * a.smax * win_h * win_w + sizeof(int) * a.smax * 3 +
+                        sizeof(unsigned int) * a.smax * ((a.smax + 31) >> 5);
+    if (smem <= 160 * 1024) {
+      static size_t attr_bytes = 0;
+      if (smem > 48 * 1024 && smem > attr_bytes) {
+        WVN_CHECK_CUDA(cudaFuncSetAttribute(segment_accumulate_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem)));
+        attr_bytes = smem;
+      }
+      dim3 grid((a.w + kTileW - 1) / kTileW, (a.h + kTileH - 1) / kTileH, a.batch);
+      segment_accumulate_tiled_kernel<<<grid, 256, smem, stream>>>(seg, a, win_h, win_w, stats, wseg, adj);
+      WVN_CHECK_LAUNCH("segment_accumulate_tiled_kernel");
+      return WVN_OK;
+    }
+  }
   const long long total = static_cast<long long>(a.batch) * a.h * a.w;
   long long blocks = (total + 255) / 256;
   const long long max_blocks = static_cast<long long>(sm_count()) * 16;
@@ -214,10 +334,21 @@ int segment_accumulate(const long long* seg, const SegmentArgs& a, unsigned long
 
 int segment_pool(const float* wseg, const float* tokens, const unsigned long long* stats, float* feat, float* centers,
                  const SegmentArgs& a, cudaStream_t stream) {
-  WVN_REQUIRE(a.dim <= 1024, "segment_pool: dim %d too large", a.dim);
-  dim3 grid(a.smax, a.batch);
-  segment_pool_kernel<<<grid, 128, 0, stream>>>(wseg, tokens, stats, feat, centers, a);
-  WVN_CHECK_LAUNCH("segment_pool_kernel");
+  if (feat) {
+    const int P = a.grid_h * a.grid_w;
+    WVN_CHECK_CUDA(cudaMemsetAsync(feat, 0, sizeof(float) * a.batch * a.smax * a.dim, stream));
+    int ksplit = (P + 447) / 448;
+    if (ksplit < 1) ksplit = 1;
+    dim3 grid((a.dim + 63) / 64, (a.smax + 31) / 32, a.batch * ksplit);
+    segment_pool_gemm_kernel<<<grid, 256, 0, stream>>>(wseg, tokens, feat, a, ksplit);
+    WVN_CHECK_LAUNCH("segment_pool_gemm_kernel");
+  }
+  if (feat || centers) {
+    const long long total = static_cast<long long>(a.batch) * a.smax * (feat ? a.dim : 1);
+    int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(sm_count()) * 8));
+    segment_finalize_kernel<<<blocks, 256, 0, stream>>>(stats, feat, centers, a);
+    WVN_CHECK_LAUNCH("segment_finalize_kernel");
+  }
   return WVN_OK;
 }
 
