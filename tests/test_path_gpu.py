@@ -163,8 +163,12 @@ def test_segment_pooling_vs_oracle(golden_dir):
     assert torch.equal(s3[0], want) and int(counts[0]) == int(want.max()) + 1
 
 
-def test_pixel_inference_vs_oracle(vit448):
+@pytest.mark.parametrize("mode", ["fused", "unfused"])
+def test_pixel_inference_vs_oracle(vit448, mode, monkeypatch):
+    """fused = algebraically restructured per-pixel head (pixel_head.cu); unfused = interp + 3 GEMMs."""
     from oracle.wvn_path import pixel_inference
+
+    monkeypatch.setenv("WVN_PIXEL_HEAD", mode)
     from wild_visual_navigation_b200 import ConfidenceGenerator, SimpleMLP, TraversabilityInference
 
     cfg, sd, di = vit448
@@ -189,7 +193,7 @@ def test_pixel_inference_vs_oracle(vit448):
                                                 mode="bilinear", align_corners=True)
         t_ref, c_ref = pixel_inference(dense, msd, cg.mean.data, cg.std.data, 0.5)
         dt, dc = (trav[b] - t_ref).abs().max().item(), (conf[b] - c_ref).abs().max().item()
-        print("pixel inference max abs diff trav/conf", dt, dc, "conf range", c_ref.min().item(), c_ref.max().item())
+        print(f"pixel inference [{mode}] max abs diff trav/conf", dt, dc, "conf range", c_ref.min().item(), c_ref.max().item())
         assert dt <= 2e-2 and dc <= 3e-2
         assert 0.02 < c_ref.float().mean() < 0.98  # the test is not saturated
 

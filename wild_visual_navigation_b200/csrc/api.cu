@@ -11,6 +11,7 @@
 #include "gemm.h"
 #include "host_common.h"
 #include "mlp_train.h"
+#include "pixel_head.h"
 #include "segment_kernels.h"
 #include "vit_kernels.h"
 
@@ -447,8 +448,14 @@ struct wvn_mlp_infer {
   int chunk_rows;
   DevBuf w1, b1, w2, b2, w3, b3;  // bf16 weights (padded / permuted), fp32 biases
   DevBuf x, a1, a2;               // bf16 activations of one chunk
+  // fused per-pixel head (pixel_head.cu): per-token GEMM operands + workspaces for kFusedFrames frames
+  DevBuf wcat, bias_cat, head_consts, tok_bf16, gu, gram;
+  int fused_tokens = 0;           // token rows the fused workspaces are sized for (grown on demand)
+  int force_unfused = 0;          // debugging / A-B knob ($WVN_PIXEL_HEAD=unfused)
   bool loaded = false;
 };
+
+static constexpr int kFusedFrames = 8;
 
 namespace {
 
@@ -547,6 +554,13 @@ int wvn_mlp_infer_create(int dim, int h1, int h2, int chunk_rows, wvn_mlp_infer_
   alloc(h->x, static_cast<size_t>(h->chunk_rows) * h->dim_p * 2);
   alloc(h->a1, static_cast<size_t>(h->chunk_rows) * h->h1_p * 2);
   alloc(h->a2, static_cast<size_t>(h->chunk_rows) * h->h2_p * 2);
+  alloc(h->wcat, static_cast<size_t>(kPixelHeadN) * h->dim_p * 2);
+  alloc(h->bias_cat, static_cast<size_t>(kPixelHeadN) * 4);
+  alloc(h->head_consts, sizeof(PixelHeadConsts));
+  {
+    const char* e = getenv("WVN_PIXEL_HEAD");
+    h->force_unfused = (e && std::string(e) == "unfused") ? 1 : 0;
+  }
   if (rc != WVN_OK) {
     wvn_mlp_infer_destroy(h);
     return rc;
@@ -557,7 +571,9 @@ int wvn_mlp_infer_create(int dim, int h1, int h2, int chunk_rows, wvn_mlp_infer_
 
 void wvn_mlp_infer_destroy(wvn_mlp_infer_t* h) {
   if (!h) return;
-  for (DevBuf* b : {&h->w1, &h->b1, &h->w2, &h->b2, &h->w3, &h->b3, &h->x, &h->a1, &h->a2}) b->release();
+  for (DevBuf* b : {&h->w1, &h->b1, &h->w2, &h->b2, &h->w3, &h->b3, &h->x, &h->a1, &h->a2, &h->wcat, &h->bias_cat,
+                    &h->head_consts, &h->tok_bf16, &h->gu, &h->gram})
+    b->release();
   delete h;
 }
 
@@ -571,6 +587,9 @@ int wvn_mlp_infer_set_params(wvn_mlp_infer_t* h, const float* params, void* stre
       reinterpret_cast<__nv_bfloat16*>(h->w2.p), reinterpret_cast<float*>(h->b2.p),
       reinterpret_cast<__nv_bfloat16*>(h->w3.p), reinterpret_cast<float*>(h->b3.p));
   WVN_CHECK_LAUNCH("pack_mlp_kernel");
+  if (h->h1 == 256 && h->h2 == 32)
+    WVN_PROPAGATE(pixel_head_pack(params, sh, h->dim_p, h->wcat.p, reinterpret_cast<float*>(h->bias_cat.p),
+                                  reinterpret_cast<PixelHeadConsts*>(h->head_consts.p), S(stream)));
   h->loaded = true;
   return WVN_OK;
 }
@@ -581,6 +600,44 @@ int wvn_mlp_infer_pixels(wvn_mlp_infer_t* h, const float* tokens, int batch, int
   WVN_REQUIRE(h && tokens && trav && conf && cg_mean && cg_std, "wvn_mlp_infer_pixels: null argument");
   if (!h->loaded) return set_error(WVN_ERR_STATE, "wvn_mlp_infer_pixels: parameters were never set");
   cudaStream_t s = S(stream);
+  const int ww = (h->force_unfused || h->dim % 64 != 0) ? 0 : pixel_head_supported(h->h1, h->h2, gh, gw, out_h, out_w);
+  if (ww > 0) {
+    // ---- fused path: per-token GEMM (G | U | cT) + token Gram, then one kernel per chunk of frames
+    const int P = gh * gw;
+    if (h->fused_tokens < kFusedFrames * P) {
+      for (DevBuf* b : {&h->tok_bf16, &h->gu, &h->gram}) b->release();
+      WVN_PROPAGATE(h->tok_bf16.alloc(static_cast<size_t>(kFusedFrames) * P * h->dim_p * 2));
+      WVN_PROPAGATE(h->gu.alloc(static_cast<size_t>(kFusedFrames) * P * kPixelHeadN * 4));
+      WVN_PROPAGATE(h->gram.alloc(static_cast<size_t>(kFusedFrames) * P * 5 * 4));
+      h->fused_tokens = kFusedFrames * P;
+    }
+    for (int b0 = 0; b0 < batch; b0 += kFusedFrames) {
+      const int nb = std::min(kFusedFrames, batch - b0);
+      const long long rows = static_cast<long long>(nb) * P;
+      const long long elems = rows * h->dim;
+      int blocks = static_cast<int>(std::min<long long>((elems + 255) / 256, 8192));
+      cast_rows_kernel<<<blocks, 256, 0, s>>>(tokens + static_cast<long long>(b0) * P * h->dim,
+                                             reinterpret_cast<__nv_bfloat16*>(h->tok_bf16.p), rows, h->dim, h->dim_p);
+      WVN_CHECK_LAUNCH("cast_rows_kernel");
+      GemmArgs g;
+      g.M = static_cast<int>(rows); g.N = kPixelHeadN; g.K = h->dim_p; g.epi = EPI_F32;
+      g.bias = reinterpret_cast<float*>(h->bias_cat.p); g.out = h->gu.p; g.ldo = kPixelHeadN;
+      WVN_PROPAGATE(gemm_bf16(g, h->tok_bf16.p, h->dim_p, h->wcat.p, 64, s));
+      WVN_PROPAGATE(token_gram(h->tok_bf16.p, reinterpret_cast<float*>(h->gram.p), nb, gh, gw, h->dim_p, s));
+      PixelHeadArgs a;
+      a.gu = reinterpret_cast<float*>(h->gu.p); a.ldg = kPixelHeadN; a.gram = reinterpret_cast<float*>(h->gram.p);
+      a.consts = reinterpret_cast<PixelHeadConsts*>(h->head_consts.p);
+      a.cg_mean = cg_mean; a.cg_std = cg_std; a.std_factor = std_factor;
+      a.trav = trav + static_cast<long long>(b0) * out_h * out_w;
+      a.conf = conf + static_cast<long long>(b0) * out_h * out_w;
+      a.batch = nb; a.gh = gh; a.gw = gw; a.H = out_h; a.W = out_w;
+      a.sy = static_cast<float>(gh - 1) / static_cast<float>(out_h - 1);
+      a.sx = static_cast<float>(gw - 1) / static_cast<float>(out_w - 1);
+      a.ww = ww; a.feat = h->dim;
+      WVN_PROPAGATE(pixel_head(a, h->w2.p, h->h1_p, s));
+    }
+    return WVN_OK;
+  }
   DenseArgs d;
   d.batch = batch; d.dim = h->dim; d.grid_h = gh; d.grid_w = gw; d.out_h = out_h; d.out_w = out_w;
   d.scale_y = out_h > 1 ? static_cast<float>(gh - 1) / static_cast<float>(out_h - 1) : 0.f;

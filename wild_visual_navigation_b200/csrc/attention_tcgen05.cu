@@ -232,30 +232,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_wait(s_full, j & 1);
       tc_fence_after();
 
-      // ---- pass 1: row max over the valid columns
+      // ---- single TMEM pass: the whole 128-wide score row of this thread goes to registers
       const bool masked = valid < kTileKV;  // only the last KV tile carries padding keys
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_s + c * 32, r);
-        tmem_ld_wait();
-        if (!masked) {
-          float m0 = -INFINITY, m1 = -INFINITY;  // two FMNMX3 chains
+      uint32_t sr[4][32];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            m0 = max3(m0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-            m1 = max3(m1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-          }
-          const float m2 = -INFINITY, m3 = -INFINITY;
-          mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-        } else {
+      for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + c * 32, sr[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);  // S(j) is in registers: QK^T(j+1) may overwrite it while we do the exps
+
+      float mx;
+      if (!masked) {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // FMNMX3 chains
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float s = __uint_as_float(r[i]);
-            mx = fmaxf(mx, (c * 32 + i < valid) ? s : -INFINITY);
-          }
+        for (int i = 0; i < 32; i += 2) {
+          m0 = max3(m0, __uint_as_float(sr[0][i]), __uint_as_float(sr[0][i + 1]));
+          m1 = max3(m1, __uint_as_float(sr[1][i]), __uint_as_float(sr[1][i + 1]));
+          m2 = max3(m2, __uint_as_float(sr[2][i]), __uint_as_float(sr[2][i + 1]));
+          m3 = max3(m3, __uint_as_float(sr[3][i]), __uint_as_float(sr[3][i + 1]));
         }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      } else {
+        mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < valid) ? __uint_as_float(sr[c][i]) : -INFINITY);
       }
 
       // ---- reference-max update (lazy: only rescale O when the max grew by > 2^8)
@@ -282,56 +284,61 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tmem_st32(tmem_o + c * 32, r);
           }
           tmem_st_wait();
+          tc_fence_before();
         }
       }
-      if (j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);  // P buffer free again
 
-      // ---- pass 2: P = exp2((s - m_ref) * sl2) -> bf16 -> swizzled smem; row sum
+      // ---- P = exp2((s - m_ref) * sl2), in place in the score registers; row sum
       const float mb = m_ref * sl2;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_s + c * 32, r);
-        tmem_ld_wait();
-        float p[32];
-        if (!masked) {
-          const uint64_t sl2_2 = pack2(sl2, sl2), nmb2 = pack2(-mb, -mb);
-          uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
+      if (!masked) {
+        const uint64_t sl2_2 = pack2(sl2, sl2), nmb2 = pack2(-mb, -mb);
+        uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const uint64_t x2 = fma2(pack2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sl2_2, nmb2);
+            const uint64_t x2 = fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sl2_2, nmb2);
+            float e0, e1;
             if (((i >> 1) & 3) < POLY) {
-              poly_exp2_pair(x2, p[i], p[i + 1]);
+              poly_exp2_pair(x2, e0, e1);
             } else {
               float x0, x1;
               unpack2(x2, x0, x1);
-              p[i] = fast_exp2(x0);
-              p[i + 1] = fast_exp2(x1);
+              e0 = fast_exp2(x0);
+              e1 = fast_exp2(x1);
             }
-            if ((i >> 1) & 1) lb = add2(lb, pack2(p[i], p[i + 1])); else la = add2(la, pack2(p[i], p[i + 1]));
-          }
-          float s0, s1;
-          unpack2(add2(la, lb), s0, s1);
-          l += s0 + s1;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            p[i] = masked_exp(__uint_as_float(r[i]), sl2, mb, c * 32 + i, valid);
-            l += p[i];
+            if ((i >> 1) & 1) lb = add2(lb, pack2(e0, e1)); else la = add2(la, pack2(e0, e1));
+            sr[c][i >> 1] = pack_bf16x2(e0, e1);  // packed bf16 pairs overwrite the consumed scores
           }
         }
-        // 32 columns = 4 x 16-byte chunks of K-block (c >> 1), chunk index (c & 1) * 4 + q
+        float s0, s1;
+        unpack2(add2(la, lb), s0, s1);
+        l += s0 + s1;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = masked_exp(__uint_as_float(sr[c][i]), sl2, mb, c * 32 + i, valid);
+            const float e1 = masked_exp(__uint_as_float(sr[c][i + 1]), sl2, mb, c * 32 + i + 1, valid);
+            l += e0 + e1;
+            sr[c][i >> 1] = pack_bf16x2(e0, e1);
+          }
+        }
+      }
+
+      if (j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);  // P buffer free again (PV(j-1) retired)
+      // ---- P -> swizzled smem: 32 columns = 4 x 16-byte chunks of K-block (c >> 1), chunk (c & 1) * 4 + q
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
         uint8_t* blk = p_row + (c >> 1) * (kPBytes / 2);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int chunk = ((c & 1) * 4 + q) ^ sw;
           *reinterpret_cast<uint4*>(blk + chunk * 16) =
-              make_uint4(pack_bf16x2(p[8 * q + 0], p[8 * q + 1]), pack_bf16x2(p[8 * q + 2], p[8 * q + 3]),
-                         pack_bf16x2(p[8 * q + 4], p[8 * q + 5]), pack_bf16x2(p[8 * q + 6], p[8 * q + 7]));
+              make_uint4(sr[c][4 * q + 0], sr[c][4 * q + 1], sr[c][4 * q + 2], sr[c][4 * q + 3]);
         }
       }
-      tc_fence_before();
-      mbar_arrive(s_free);        // S(j) fully read: QK^T(j+1) may overwrite it
       fence_proxy_async_smem();   // P(j) visible to the tensor core (async proxy)
       mbar_arrive(p_full);
     }

@@ -47,6 +47,9 @@ struct GemmArgs {
   float cg_std_factor = 0.5f;
   // launch control
   int max_ctas = 0;             // 0 = one CTA per SM
+  int allow_b_resident = 1;     // let the launcher pin the weight slab in smem when it fits
+  int b_resident = 0;           // (set by the launcher)
+  int a_stages = 0;             // (set by the launcher)
 };
 
 int pick_block_n(int N);

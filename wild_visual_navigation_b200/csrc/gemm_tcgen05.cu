@@ -12,6 +12,8 @@
 //   warp 1      : MMA issuer     (single thread issues tcgen05.mma, commits to mbarriers)
 //   warp 2      : TMEM allocator (2 accumulator stages so epilogue(i) overlaps mainloop(i+1))
 //   warps 4..11 : epilogue       (tcgen05.ld -> bias/activation/residual -> global)
+#include <algorithm>
+
 #include "common.cuh"
 #include "gemm.h"
 #include "host_common.h"
@@ -25,21 +27,29 @@ constexpr int BK = 64;
 constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiThreads = 256;
+constexpr int kMaxSmemBytes = 227 * 1024;
 
 // Tile enumeration.  Default: tile ids run n-fastest over the whole (m, n) grid and are
 // dealt round-robin to CTAs (neighbouring CTAs share the A tile through L2).  ROW_OWNER
 // (used by EPI_MLP_HEAD): a CTA owns whole 128-row blocks and visits their n-chunks in
 // order, so per-row reductions across n-chunks stay inside one CTA.
+// B_RESIDENT (runtime, K small): a CTA is pinned to one n-block whose whole [BN, K] weight slab
+// stays in shared memory; it walks the m-blocks slot, slot + S, ... (S = gridDim.x / num_n), so only
+// the activation tiles stream through L2 -> smem (the L2 -> SM path, ~42 B/clk/SM, is what bounds
+// these skinny-K GEMMs, not the tensor pipe).
 template <bool ROW_OWNER>
 struct TileIter {
-  int num_m, num_n, m_blk, n_blk, lin;
-  __device__ TileIter(int nm, int nn) : num_m(nm), num_n(nn), m_blk(0), n_blk(0) {
-    if (ROW_OWNER) { m_blk = blockIdx.x; n_blk = 0; }
+  int num_m, num_n, m_blk, n_blk, lin, step;
+  bool bres;
+  __device__ TileIter(int nm, int nn, bool b_resident) : num_m(nm), num_n(nn), m_blk(0), n_blk(0), lin(0), step(0), bres(b_resident) {
+    if (bres) { n_blk = blockIdx.x % num_n; m_blk = blockIdx.x / num_n; step = gridDim.x / num_n; }
+    else if (ROW_OWNER) { m_blk = blockIdx.x; n_blk = 0; }
     else { lin = blockIdx.x; m_blk = lin / num_n; n_blk = lin % num_n; }
   }
   __device__ bool valid() const { return m_blk < num_m; }
   __device__ void next() {
-    if (ROW_OWNER) { if (++n_blk == num_n) { n_blk = 0; m_blk += gridDim.x; } }
+    if (bres) { m_blk += step; }
+    else if (ROW_OWNER) { if (++n_blk == num_n) { n_blk = 0; m_blk += gridDim.x; } }
     else { lin += gridDim.x; m_blk = lin / num_n; n_blk = lin % num_n; }
   }
 };
@@ -66,18 +76,23 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmArgs args) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::kStages;
+  constexpr int kMaxStages = 8;
+  const bool bres = args.b_resident != 0;
+  // streaming mode: STAGES x (A, B) slots; B-resident mode: the [BN, K] slab + an A-only ring
+  const int STAGES = bres ? args.a_stages : Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;                  // [STAGES]  TMA -> MMA
-  uint64_t* empty_bar = bars + STAGES;        // [STAGES]  MMA -> TMA
-  uint64_t* acc_full = bars + 2 * STAGES;     // [2]       MMA -> epilogue
-  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]     epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t b_region = bres ? static_cast<uint32_t>(args.K / BK) * Cfg::kBBytes : static_cast<uint32_t>(STAGES) * Cfg::kBBytes;
+  uint8_t* smem_b = smem;
+  uint8_t* smem_a = smem + b_region;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + STAGES * Cfg::kABytes);
+  uint64_t* full_bar = bars;                       // [kMaxStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * kMaxStages;      // [2]           MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * kMaxStages + 2; // [2]           epilogue -> MMA
+  uint64_t* b_full = bars + 2 * kMaxStages + 4;    // [1]           resident weight slab landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,14 +101,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int num_n = args.N / BN;
   const int num_k = args.K / BK;
   constexpr bool ROW_OWNER = (EPI == EPI_MLP_HEAD);
-  float* row_acc = reinterpret_cast<float*>(bars + 2 * STAGES + 6);  // [128] EPI_MLP_HEAD scratch
+  float* row_acc = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);  // [128] EPI_MLP_HEAD scratch
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -101,6 +116,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], kNumEpiThreads);
     }
+    mbar_init(b_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -114,13 +130,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (TileIter<ROW_OWNER> it(num_m, num_n); it.valid(); it.next()) {
+      if (bres) {
+        const int n_blk = blockIdx.x % num_n;
+        mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(num_k) * Cfg::kBBytes);
+        for (int kb = 0; kb < num_k; ++kb)
+          tma_load_2d(&tmap_b, b_full, smem_b + kb * Cfg::kBBytes, kb * BK, n_blk * BN);
+      }
+      for (TileIter<ROW_OWNER> it(num_m, num_n, bres); it.valid(); it.next()) {
         const int m_blk = it.m_blk, n_blk = it.n_blk;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          mbar_arrive_expect_tx(&full_bar[stage], bres ? Cfg::kABytes : Cfg::kStageBytes);
           tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * BK, m_blk * BM);
-          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * BK, n_blk * BN);
+          if (!bres) tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -133,7 +155,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (TileIter<ROW_OWNER> it(num_m, num_n); it.valid(); it.next()) {
+      if (bres) mbar_wait(b_full, 0);
+      for (TileIter<ROW_OWNER> it(num_m, num_n, bres); it.valid(); it.next()) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -141,7 +164,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+          const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + (bres ? kb : stage) * Cfg::kBBytes));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in (addr>>4) units
@@ -164,7 +187,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     float head_partial = 0.f;
     if (EPI == EPI_MLP_HEAD && half == 0) row_acc[row_in_tile] = 0.f;
     if (EPI == EPI_MLP_HEAD) asm volatile("bar.sync 1, 256;" ::: "memory");
-    for (TileIter<ROW_OWNER> it(num_m, num_n); it.valid(); it.next()) {
+    for (TileIter<ROW_OWNER> it(num_m, num_n, bres); it.valid(); it.next()) {
       const int m_blk = it.m_blk, n_blk = it.n_blk;
       const int row = m_blk * BM + row_in_tile;
       const bool row_ok = row < args.M;
@@ -318,7 +341,7 @@ int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
   auto kern = gemm_bf16_kernel<BN, EPI, ACT>;
   static bool attr_set = false;
   if (!attr_set) {
-    WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
     attr_set = true;
   }
   const int num_tiles = (EPI == EPI_MLP_HEAD) ? (a.M + BM - 1) / BM : ((a.M + BM - 1) / BM) * (a.N / BN);
@@ -373,7 +396,12 @@ int pick_block_n(int N) {
 int gemm_bf16(const GemmArgs& a, const void* A, long long lda, const void* W, int block_n, cudaStream_t stream) {
   WVN_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem (M=%d N=%d K=%d)", a.M, a.N, a.K);
   WVN_REQUIRE(a.K % BK == 0, "gemm: K=%d must be a multiple of %d (pad the operands)", a.K, BK);
-  if (block_n == 0) block_n = pick_block_n(a.N);
+  if (block_n == 0) {
+    block_n = pick_block_n(a.N);
+    // prefer a 192-wide tile whose [192, K] weight slab can stay resident in shared memory
+    if (a.allow_b_resident && a.epi != EPI_MLP_HEAD && a.N % 192 == 0 && (a.K / BK) * 192 * 128 + 3 * 16384 + 2048 <= kMaxSmemBytes)
+      block_n = 192;
+  }
   WVN_REQUIRE(block_n == 64 || block_n == 128 || block_n == 192 || block_n == 224 || block_n == 256,
               "gemm: bad block_n %d", block_n);
   WVN_REQUIRE(a.N % block_n == 0, "gemm: N=%d must be a multiple of block_n=%d (pad the weights)", a.N, block_n);
