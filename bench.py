@@ -197,24 +197,64 @@ def run_b200(args):
         ti.refresh_weights()                                       # inference sees the updated MLP
         return trav, conf
 
+    # end-to-end leg: every step copies its frames host->device (pinned) and its maps + loss metrics
+    # device->host, on copy streams so that step k's transfers overlap step k-1 / k+1's compute
+    # (double-buffered, exactly what a camera loop around the public API would do).
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    img_buf = [torch.empty(B, 3, IMG, IMG, device=dev) for _ in range(2)]
+    out_buf = [(torch.empty(B, IMG, IMG, device=dev), torch.empty(B, IMG, IMG, device=dev), torch.empty(6, device=dev))
+               for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_used = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    state = {"primed": False}
+
+    def h2d(k):
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_used[k % 2])                        # compute no longer reads this buffer
+            img_buf[k % 2].copy_(host_imgs[k % 3], non_blocking=True)
+            ev_in[k % 2].record(s_in)
+
     def step_e2e(k):
-        img = host_imgs[k % 3].to(dev, non_blocking=True)          # H2D of this step's frames (pinned)
-        trav, conf = step(img)
-        host_trav.copy_(trav, non_blocking=True)                   # D2H of the per-pixel maps
-        host_conf.copy_(conf, non_blocking=True)
-        host_metrics.copy_(te._trainer.metrics, non_blocking=True)
+        cur = torch.cuda.current_stream()
+        if not state["primed"]:
+            h2d(k)
+            state["primed"] = True
+        cur.wait_event(ev_in[k % 2])
+        h2d(k + 1)                                                 # prefetch the next step's frames
+        trav, conf = step(img_buf[k % 2])
+        ev_used[k % 2].record(cur)
+        cur.wait_event(ev_out[k % 2])                              # previous D2H out of this slot finished
+        out_buf[k % 2][0].copy_(trav)
+        out_buf[k % 2][1].copy_(conf)
+        out_buf[k % 2][2].copy_(te._trainer.metrics)
+        ev_done[k % 2].record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_done[k % 2])
+            host_trav.copy_(out_buf[k % 2][0], non_blocking=True)  # D2H of the per-pixel maps + metrics
+            host_conf.copy_(out_buf[k % 2][1], non_blocking=True)
+            host_metrics.copy_(out_buf[k % 2][2], non_blocking=True)
+            ev_out[k % 2].record(s_out)
+
+    def drain_e2e():
+        torch.cuda.current_stream().wait_stream(s_out)
+        torch.cuda.current_stream().wait_stream(s_in)
+        state["primed"] = False
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for k in range(steps):
             fn(k)
+        if finish is not None:
+            finish()                                               # the last D2H is inside the timed region
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -232,6 +272,7 @@ def run_b200(args):
         return
     for k in range(min(2, args.warmup)):
         step_e2e(k)
+    drain_e2e()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -245,7 +286,7 @@ def run_b200(args):
     prof_n = (ctypes.c_longlong * 2)()
     _C.check(lib.wvn_profile_collect(prof_ms, prof_n))
     lib.wvn_profile_enable(0)
-    e2e_ms = timed(step_e2e, args.steps)
+    e2e_ms = timed(step_e2e, args.steps, finish=drain_e2e)
     clocks = sampler.stop() if rank == 0 else None
 
     ms_per_step = total_ms / args.steps
@@ -303,7 +344,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--chunk", type=int, default=8, help="frames per ViT activation chunk")
+    ap.add_argument("--chunk", type=int, default=32, help="frames per ViT activation chunk")
     ap.add_argument("--cpu-frames", type=int, default=1, help="frames in the bounded CPU sample (5.7 s/frame on 8 cores)")
     ap.add_argument("--cpu-threads", type=int, default=32,
                     help="torch CPU threads for the CPU legs (more than ~32 only adds sync overhead on these small ops)")

@@ -135,9 +135,10 @@ int wvn_vit_npad(const wvn_vit_t* h);
 int wvn_upsample_dense(const float* tokens, float* out, int batch, int dim, int gh, int gw, int out_h, int out_w,
                        void* stream);
 /* bilinear (align_corners=False) upsampling of per-patch logits + argmax -> int64 segment ids
- * (STEGO postprocess + stego_interface.py:108-109).  logits: [batch*npad, ld] fp32. */
-int wvn_logits_argmax(const float* logits, long long ld, int col0, int classes, int batch, int npad, int gh, int gw,
-                      int out_h, int out_w, long long* seg, void* stream);
+ * (STEGO postprocess + stego_interface.py:108-109).  logits: [batch*npad, ld] fp32.  Two logit
+ * column ranges (cluster probe -> seg, linear probe -> seg_b; seg_b may be NULL) share one pass. */
+int wvn_logits_argmax(const float* logits, long long ld, int col0, int classes, int col0_b, int classes_b, int batch,
+                      int npad, int gh, int gw, int out_h, int out_w, long long* seg, long long* seg_b, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Segment reductions — replace SegmentExtractor.adjacency_list / .centers

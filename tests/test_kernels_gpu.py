@@ -25,7 +25,7 @@ def ops():
 
 @pytest.mark.parametrize("M,N,K,bn", [
     (128, 128, 64, 128), (300, 384, 384, 0), (1000, 1152, 384, 192), (777, 1536, 384, 256), (512, 384, 1536, 0),
-    (130, 448, 64, 224), (4096, 64, 256, 64), (128 * 150, 384, 192, 128),
+    (130, 448, 64, 224), (4096, 64, 256, 64), (128 * 150, 384, 192, 128), (25600, 1152, 384, 0), (12800, 1536, 384, 0),
 ])
 @pytest.mark.parametrize("out_kind,act", [(0, 0), (0, 1), (0, 2), (1, 0), (2, 0)])
 def test_gemm(ops, M, N, K, bn, out_kind, act):
@@ -121,8 +121,8 @@ def test_logits_argmax_matches_upstream_order(ops):
     B, g, K, npad = 2, 7, 11, 128
     logits = torch.zeros(B * npad, 64, device="cuda")
     grid = torch.randn(B, g * g, K, device="cuda")
-    logits.view(B, npad, 64)[:, 1 : 1 + g * g, 5 : 5 + K] = grid
-    seg = ops.logits_argmax(logits, 5, K, B, npad, g, g, 56, 56)
+    logits.view(B, npad, 64)[:, 1 : 1 + g * g, 8 : 8 + K] = grid
+    seg = ops.logits_argmax(logits, 8, K, B, npad, g, g, 56, 56)
     ref = torch.nn.functional.interpolate(grid.reshape(B, g, g, K).permute(0, 3, 1, 2), (56, 56), mode="bilinear",
                                           align_corners=False).argmax(1)
     assert (seg == ref).float().mean() > 0.999

@@ -55,7 +55,7 @@ SIGNATURES = {
     "wvn_vit_stego_head": (_I, [_P, _I, _P, _P]),
     "wvn_vit_npad": (_I, [_P]),
     "wvn_upsample_dense": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "wvn_logits_argmax": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "wvn_logits_argmax": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "wvn_segment_workspace_bytes": (_S, [_I, _I, _I, _I]),
     "wvn_segment_reduce": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
     "wvn_segment_relabel": (_I, [_P, _I, _L, _I, _P, _P, _P]),

@@ -384,14 +384,14 @@ int wvn_upsample_dense(const float* tokens, float* out, int batch, int dim, int 
   return upsample_tokens_dense(tokens, out, a, S(stream));
 }
 
-int wvn_logits_argmax(const float* logits, long long ld, int col0, int classes, int batch, int npad, int gh, int gw,
-                      int out_h, int out_w, long long* seg, void* stream) {
+int wvn_logits_argmax(const float* logits, long long ld, int col0, int classes, int col0_b, int classes_b, int batch,
+                      int npad, int gh, int gw, int out_h, int out_w, long long* seg, long long* seg_b, void* stream) {
   LogitsArgs a;
   a.batch = batch; a.classes = classes; a.grid_h = gh; a.grid_w = gw; a.out_h = out_h; a.out_w = out_w;
   a.scale_y = static_cast<float>(gh) / static_cast<float>(out_h);
   a.scale_x = static_cast<float>(gw) / static_cast<float>(out_w);
-  a.npad = npad; a.ld = ld; a.col0 = col0;
-  return logits_argmax(logits, seg, a, S(stream));
+  a.npad = npad; a.ld = ld; a.col0 = col0; a.col0_b = col0_b; a.classes_b = classes_b;
+  return logits_argmax(logits, seg, seg_b, a, S(stream));
 }
 
 // -------------------------------------------------------------------------------- segments

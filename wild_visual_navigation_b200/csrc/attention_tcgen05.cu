@@ -44,7 +44,9 @@ constexpr uint32_t kSmemBytes = kOffBar + 256;
 constexpr uint32_t kTmemCols = 256;  // S: [0,128)  O: [128,192)
 constexpr uint32_t kColS = 0;
 constexpr uint32_t kColO = 128;
+constexpr uint32_t kColMail = 192;  // 6 mailbox columns: [parity 0/1][half 0/1] row maxima, then [half] row sums
 constexpr float kRescaleThreshold = 8.0f;  // in log2 units (FA4-style lazy rescale)
+constexpr int kDefaultSplit = 1;
 constexpr int kDefaultPoly = 0;            // software-exp2 share: pairs out of every 4 pairs (see poly_exp2_pair)
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -102,8 +104,12 @@ __device__ __forceinline__ float masked_exp(float s, float sl2, float mb, int co
   return (col < valid) ? fast_exp2(fmaf(s, sl2, -mb)) : 0.f;
 }
 
-template <int POLY>
-__global__ void __launch_bounds__(kThreads, 2)
+// SPLIT = threads per query row in the softmax phase.  SPLIT == 2 gives each row to two threads of
+// different warps (64 key columns each): twice the softmax warps per SM to hide the TMEM-load /
+// MUFU / barrier latencies, half the registers per thread; the two halves agree on the reference
+// max through a one-column mailbox in tensor memory (shared memory is full at 2 CTAs/SM).
+template <int POLY, int SPLIT>
+__global__ void __launch_bounds__(64 + 128 * SPLIT, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_vt, const AttnArgs args) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -138,8 +144,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_free, 128 * SPLIT);
+    mbar_init(p_full, 128 * SPLIT);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -212,6 +218,163 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         umma_commit(&v_empty[st]);
         umma_commit(pv_done);
       }
+    }
+  } else if (SPLIT == 2) {
+    // -------------------------------------------------------------- softmax, two threads per row
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;       // which 64 key columns of every tile (= P's K-block)
+    const int row = quarter * 32 + lane;    // row inside the query tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tmem_s = tmem_base + lane_base + kColS + half * 64;
+    const uint32_t tmem_o = tmem_base + lane_base + kColO + half * 32;
+    const uint32_t tmem_mail = tmem_base + lane_base + kColMail;  // [parity][half] mailbox columns
+    uint8_t* p_row = smem + kOffP + half * (kPBytes / 2) + row * 128;
+    const int sw = row & 7;
+    const float sl2 = args.scale_log2;
+    float m_ref = -INFINITY, l = 0.f;
+
+    for (int j = 0; j < nkv; ++j) {
+      const int valid = args.n_valid - j * kTileKV - half * 64;  // valid columns of this half
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t sr[2][32];
+      tmem_ld32(tmem_s, sr[0]);
+      tmem_ld32(tmem_s + 32, sr[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);
+
+      const bool masked = valid < 64;
+      float mx;
+      if (!masked) {
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          m0 = max3(m0, __uint_as_float(sr[0][i]), __uint_as_float(sr[0][i + 1]));
+          m1 = max3(m1, __uint_as_float(sr[1][i]), __uint_as_float(sr[1][i + 1]));
+        }
+        mx = fmaxf(m0, m1);
+      } else {
+        mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < valid) ? __uint_as_float(sr[c][i]) : -INFINITY);
+      }
+      // exchange the half-row maxima with the partner thread (same row, other half) through TMEM
+      const uint32_t mail = tmem_mail + (j & 1) * 2;
+      tmem_st1(mail + half, __float_as_uint(mx));
+      tmem_st_wait();
+      tc_fence_before();
+      named_bar_sync(1 + quarter, 64);
+      tc_fence_after();
+      mx = fmaxf(mx, __uint_as_float(tmem_ld1(mail + (half ^ 1))));
+      tmem_ld_wait();
+
+      bool waited_pv = false;
+      if (j == 0) {
+        m_ref = mx;
+      } else {
+        const float m_new = fmaxf(m_ref, mx);
+        const bool need = (m_new - m_ref) * sl2 > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(pv_done, (j - 1) & 1);
+          waited_pv = true;
+          tc_fence_after();
+          const float alpha = need ? fast_exp2((m_ref - m_new) * sl2) : 1.f;
+          if (need) m_ref = m_new;
+          l *= alpha;
+          uint32_t r[32];
+          tmem_ld32(tmem_o, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st32(tmem_o, r);
+          tmem_st_wait();
+          tc_fence_before();
+        }
+      }
+
+      const float mb = m_ref * sl2;
+      if (!masked) {
+        const uint64_t sl2_2 = pack2(sl2, sl2), nmb2 = pack2(-mb, -mb);
+        uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint64_t x2 = fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sl2_2, nmb2);
+            float e0, e1;
+            if (POLY == 9) {  // timing experiment only: no exponentials at all (results are wrong)
+              unpack2(x2, e0, e1);
+            } else if (((i >> 1) & 3) < POLY) {
+              poly_exp2_pair(x2, e0, e1);
+            } else {
+              float x0, x1;
+              unpack2(x2, x0, x1);
+              e0 = fast_exp2(x0);
+              e1 = fast_exp2(x1);
+            }
+            if ((i >> 1) & 1) lb = add2(lb, pack2(e0, e1)); else la = add2(la, pack2(e0, e1));
+            sr[c][i >> 1] = pack_bf16x2(e0, e1);
+          }
+        }
+        float s0, s1;
+        unpack2(add2(la, lb), s0, s1);
+        l += s0 + s1;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = masked_exp(__uint_as_float(sr[c][i]), sl2, mb, c * 32 + i, valid);
+            const float e1 = masked_exp(__uint_as_float(sr[c][i + 1]), sl2, mb, c * 32 + i + 1, valid);
+            l += e0 + e1;
+            sr[c][i >> 1] = pack_bf16x2(e0, e1);
+          }
+        }
+      }
+
+      if (j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);
+      // this half's 64 columns are exactly K-block `half` of P: 8 swizzled 16-byte chunks
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (c * 4 + q) ^ sw;
+          *reinterpret_cast<uint4*>(p_row + chunk * 16) =
+              make_uint4(sr[c][4 * q + 0], sr[c][4 * q + 1], sr[c][4 * q + 2], sr[c][4 * q + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+    }
+
+    // ---- epilogue: combine the two partial row sums, O / l for this half's 32 output columns
+    mbar_wait(pv_done, (nkv - 1) & 1);
+    tc_fence_after();
+    tmem_st1(tmem_mail + 4 + half, __float_as_uint(l));
+    tmem_st_wait();
+    tc_fence_before();
+    named_bar_sync(1 + quarter, 64);
+    tc_fence_after();
+    l += __uint_as_float(tmem_ld1(tmem_mail + 4 + (half ^ 1)));
+    tmem_ld_wait();
+    const float inv_l = 1.f / l;
+    const int b = bh / args.heads;
+    const int h = bh - b * args.heads;
+    const long long q_idx = static_cast<long long>(b) * args.npad + q_tile * kTileQ + row;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + q_idx * args.ldo + h * kDh + half * 32;
+    uint32_t r[32];
+    tmem_ld32(tmem_o, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[8 * q + i]) * inv_l;
+      st_global_v4(dst + 8 * q, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                   pack_bf16x2(f[6], f[7]));
     }
   } else {
     // -------------------------------------------------------------- softmax / correction / epilogue
@@ -299,7 +462,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           for (int i = 0; i < 32; i += 2) {
             const uint64_t x2 = fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sl2_2, nmb2);
             float e0, e1;
-            if (((i >> 1) & 3) < POLY) {
+            if (POLY == 9) {  // timing experiment only: no exponentials at all (results are wrong)
+              unpack2(x2, e0, e1);
+            } else if (((i >> 1) & 3) < POLY) {
               poly_exp2_pair(x2, e0, e1);
             } else {
               float x0, x1;
@@ -392,21 +557,35 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
   if (poly < 0) {
     const char* e = getenv("WVN_ATTN_POLY");
     poly = e ? atoi(e) : kDefaultPoly;
-    if (poly < 0 || poly > 3) poly = kDefaultPoly;
+    if ((poly < 0 || poly > 3) && poly != 9) poly = kDefaultPoly;
+  }
+  static int split = -1;
+  if (split < 0) {
+    const char* e = getenv("WVN_ATTN_SPLIT");
+    split = e ? atoi(e) : kDefaultSplit;
+    if (split != 1 && split != 2) split = kDefaultSplit;
   }
   dim3 grid(a.npad / kTileQ, static_cast<unsigned>(bh));
-  auto launch = [&](auto kern) -> int {
+  auto launch = [&](auto kern, int threads) -> int {
     WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     prof_begin(PROF_ATTENTION, stream);
-    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, a);
+    kern<<<grid, threads, kSmemBytes, stream>>>(tq, tk, tv, a);
     prof_end(PROF_ATTENTION, stream);
     return WVN_OK;
   };
-  switch (poly) {
-    case 0: WVN_PROPAGATE(launch(attention_kernel<0>)); break;
-    case 1: WVN_PROPAGATE(launch(attention_kernel<1>)); break;
-    case 2: WVN_PROPAGATE(launch(attention_kernel<2>)); break;
-    default: WVN_PROPAGATE(launch(attention_kernel<3>)); break;
+  if (split == 2) {
+    switch (poly) {
+      case 0: WVN_PROPAGATE(launch(attention_kernel<0, 2>, 320)); break;
+      case 1: WVN_PROPAGATE(launch(attention_kernel<1, 2>, 320)); break;
+      default: WVN_PROPAGATE(launch(attention_kernel<2, 2>, 320)); break;
+    }
+  } else {
+    switch (poly) {
+      case 0: WVN_PROPAGATE(launch(attention_kernel<0, 1>, 192)); break;
+      case 1: WVN_PROPAGATE(launch(attention_kernel<1, 1>, 192)); break;
+      case 9: WVN_PROPAGATE(launch(attention_kernel<9, 1>, 192)); break;
+      default: WVN_PROPAGATE(launch(attention_kernel<2, 1>, 192)); break;
+    }
   }
   WVN_CHECK_LAUNCH("attention_kernel");
   return WVN_OK;

@@ -108,10 +108,12 @@ interp_pixel_rows_kernel(const float* __restrict__ tok, __nv_bfloat16* __restric
   }
 }
 
-// One thread per output pixel: bilinear blend of K logits from the 4 neighbouring patches,
-// running argmax (first maximum wins, like torch.argmax).
+// One thread per output pixel: bilinear blend of the class logits of the 4 neighbouring patches
+// (float4 loads), running argmax (first maximum wins, like torch.argmax).  Up to two logit ranges
+// (STEGO cluster probe and linear probe) are resolved in the same pass.
 __global__ void __launch_bounds__(256)
-logits_argmax_kernel(const float* __restrict__ logits, long long* __restrict__ seg, LogitsArgs a) {
+logits_argmax_kernel(const float* __restrict__ logits, long long* __restrict__ seg_a, long long* __restrict__ seg_b,
+                     LogitsArgs a) {
   const long long total = static_cast<long long>(a.batch) * a.out_h * a.out_w;
   for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
        p += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -122,20 +124,39 @@ logits_argmax_kernel(const float* __restrict__ logits, long long* __restrict__ s
     float wx, wy;
     ac_false_coord(x, a.scale_x, a.grid_w, x0, x1, wx);
     ac_false_coord(y, a.scale_y, a.grid_h, y0, y1, wy);
+    const float w00 = (1.f - wy) * (1.f - wx), w01 = (1.f - wy) * wx, w10 = wy * (1.f - wx), w11 = wy * wx;
     // token row of patch (gy, gx) in the padded activation layout: b*npad + 1 + gy*gw + gx
-    const float* base = logits + (b * a.npad + 1) * a.ld + a.col0;
+    const float* base = logits + (b * a.npad + 1) * a.ld;
     const float* r00 = base + (static_cast<long long>(y0) * a.grid_w + x0) * a.ld;
     const float* r01 = base + (static_cast<long long>(y0) * a.grid_w + x1) * a.ld;
     const float* r10 = base + (static_cast<long long>(y1) * a.grid_w + x0) * a.ld;
     const float* r11 = base + (static_cast<long long>(y1) * a.grid_w + x1) * a.ld;
-    float best = -INFINITY;
-    int arg = 0;
-    for (int k = 0; k < a.classes; ++k) {
-      const float v = (1.f - wy) * ((1.f - wx) * __ldg(r00 + k) + wx * __ldg(r01 + k)) +
-                      wy * ((1.f - wx) * __ldg(r10 + k) + wx * __ldg(r11 + k));
-      if (v > best) { best = v; arg = k; }
+#pragma unroll
+    for (int range = 0; range < 2; ++range) {
+      const int col0 = range == 0 ? a.col0 : a.col0_b;
+      const int classes = range == 0 ? a.classes : a.classes_b;
+      long long* out = range == 0 ? seg_a : seg_b;
+      if (out == nullptr || classes <= 0) continue;
+      float best = -INFINITY;
+      int arg = 0;
+      for (int k4 = 0; k4 < classes; k4 += 4) {
+        const float4 a00 = __ldg(reinterpret_cast<const float4*>(r00 + col0 + k4));
+        const float4 a01 = __ldg(reinterpret_cast<const float4*>(r01 + col0 + k4));
+        const float4 a10 = __ldg(reinterpret_cast<const float4*>(r10 + col0 + k4));
+        const float4 a11 = __ldg(reinterpret_cast<const float4*>(r11 + col0 + k4));
+        // same grouping as ATen: blend x inside each row, then y  ((1-wy)*((1-wx)a+wx b) + wy*(...))
+        const float v[4] = {
+            (1.f - wy) * ((1.f - wx) * a00.x + wx * a01.x) + wy * ((1.f - wx) * a10.x + wx * a11.x),
+            (1.f - wy) * ((1.f - wx) * a00.y + wx * a01.y) + wy * ((1.f - wx) * a10.y + wx * a11.y),
+            (1.f - wy) * ((1.f - wx) * a00.z + wx * a01.z) + wy * ((1.f - wx) * a10.z + wx * a11.z),
+            (1.f - wy) * ((1.f - wx) * a00.w + wx * a01.w) + wy * ((1.f - wx) * a10.w + wx * a11.w)};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (k4 + i < classes && v[i] > best) { best = v[i]; arg = k4 + i; }
+      }
+      out[p] = arg;
     }
-    seg[p] = arg;
+    (void)w00; (void)w01; (void)w10; (void)w11;
   }
 }
 
@@ -163,13 +184,14 @@ int interp_pixel_rows(const float* tokens, void* out_bf16, const DenseArgs& a, l
   return WVN_OK;
 }
 
-int logits_argmax(const float* logits, long long* seg, const LogitsArgs& a, cudaStream_t stream) {
+int logits_argmax(const float* logits, long long* seg, long long* seg_b, const LogitsArgs& a, cudaStream_t stream) {
   WVN_REQUIRE(a.classes > 0 && a.batch > 0, "logits_argmax: empty problem");
+  WVN_REQUIRE(a.col0 % 4 == 0 && a.col0_b % 4 == 0 && a.ld % 4 == 0, "logits_argmax: columns must be float4-aligned");
   const long long total = static_cast<long long>(a.batch) * a.out_h * a.out_w;
   long long blocks = (total + 255) / 256;
   const long long max_blocks = static_cast<long long>(sm_count()) * 16;
   if (blocks > max_blocks) blocks = max_blocks;
-  logits_argmax_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(logits, seg, a);
+  logits_argmax_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(logits, seg, seg_b, a);
   WVN_CHECK_LAUNCH("logits_argmax_kernel");
   return WVN_OK;
 }

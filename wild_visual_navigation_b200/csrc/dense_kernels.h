@@ -22,13 +22,14 @@ struct LogitsArgs {
   float scale_y = 0.f, scale_x = 0.f;  // grid/out, align_corners=False
   int npad = 0;                // rows per frame of the logits matrix (row 0 = CLS)
   long long ld = 0;            // row pitch of the logits matrix
-  int col0 = 0;                // first logit column
+  int col0 = 0;                // first logit column (multiple of 4)
+  int col0_b = 0, classes_b = 0;  // optional second logit range resolved in the same pass
 };
 
 // tokens: [B, grid_h*grid_w, dim] fp32 (CLS already dropped).
 int upsample_tokens_dense(const float* tokens, float* out_nchw, const DenseArgs& a, cudaStream_t stream);
 int interp_pixel_rows(const float* tokens, void* out_bf16, const DenseArgs& a, long long pix0, long long npix,
                       cudaStream_t stream);
-int logits_argmax(const float* logits, long long* seg, const LogitsArgs& a, cudaStream_t stream);
+int logits_argmax(const float* logits, long long* seg, long long* seg_b, const LogitsArgs& a, cudaStream_t stream);
 
 }  // namespace wvn

@@ -47,7 +47,7 @@ struct GemmArgs {
   float cg_std_factor = 0.5f;
   // launch control
   int max_ctas = 0;             // 0 = one CTA per SM
-  int allow_b_resident = 1;     // let the launcher pin the weight slab in smem when it fits
+  int allow_b_resident = 0;     // let the launcher pin the weight slab in smem when it fits (measured slower on B200: off)
   int b_resident = 0;           // (set by the launcher)
   int a_stages = 0;             // (set by the launcher)
 };

@@ -12,6 +12,8 @@
 //   warp 1      : MMA issuer     (single thread issues tcgen05.mma, commits to mbarriers)
 //   warp 2      : TMEM allocator (2 accumulator stages so epilogue(i) overlaps mainloop(i+1))
 //   warps 4..11 : epilogue       (tcgen05.ld -> bias/activation/residual -> global)
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -28,6 +30,7 @@ constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiThreads = 256;
 constexpr int kMaxSmemBytes = 227 * 1024;
+constexpr int kFixedSmemBytes = 1024 /*barriers + scratch*/ + 1024 /*align slack*/;
 
 // Tile enumeration.  Default: tile ids run n-fastest over the whole (m, n) grid and are
 // dealt round-robin to CTAs (neighbouring CTAs share the A tile through L2).  ROW_OWNER
@@ -62,12 +65,28 @@ struct GemmCfg {
   static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kFixedSmemBytes;
 };
+
+// GELU(x) = x * Phi(x) with the erf form's Phi, evaluated as Phi(-|x|) = 2^p(|x|) (degree-5 minimax fit of
+// log2 Phi(-t) on [0, 5.5], clamped beyond): max |error| 1.5e-6 in GELU — three orders below the bf16
+// rounding of the output — at 1 MUFU + ~9 FMA/ALU ops instead of erff's ~30 (the fc1 epilogue was
+// issue-bound on erff).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float t = fminf(fabsf(x), 5.5f);
+  float p = fmaf(-0.0003865310864f, t, 0.006509808358f);
+  p = fmaf(p, t, -0.05048002675f);
+  p = fmaf(p, t, -0.4613505006f);
+  p = fmaf(p, t, -1.150225043f);
+  p = fmaf(p, t, -1.00010848f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p));
+  return x * (x >= 0.f ? 1.f - e : e);
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (act == ACT_GELU) return gelu_erf_fast(v);
   return v;
 }
 
@@ -191,6 +210,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m_blk = it.m_blk, n_blk = it.n_blk;
       const int row = m_blk * BM + row_in_tile;
       const bool row_ok = row < args.M;
+      // Residual epilogue: fetch this thread's slice of the residual row BEFORE waiting for the
+      // accumulator, so the global-load latency hides behind the tile's MMA time.
+      constexpr bool kPreloadResid = (EPI == EPI_RESID_F32) && (BN <= 192);
+      constexpr int kChunksPerThread = (BN + 63) / 64;
+      float4 resid_pre[kPreloadResid ? kChunksPerThread : 1][8];
+      if (kPreloadResid && row_ok) {
+#pragma unroll
+        for (int ci = 0; ci < kChunksPerThread; ++ci) {
+          const int c0 = half * 32 + 64 * ci;
+          if (c0 < BN) {
+            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(args.out) +
+                                                               static_cast<long long>(row) * args.ldo + n_blk * BN + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) resid_pre[ci][j] = src[j];
+          }
+        }
+      }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
 
@@ -206,8 +242,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tok = row - frame * args.npad;
       }
 
-#pragma unroll 1
-      for (int c0 = half * 32; c0 < BN; c0 += 64) {  // the two column-halves interleave 32-col chunks
+#pragma unroll
+      for (int chunk_i = 0; chunk_i < kChunksPerThread; ++chunk_i) {  // the two column-halves interleave 32-col chunks
+        const int c0 = half * 32 + 64 * chunk_i;
+        if (c0 >= BN) break;
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c0, r);
         tmem_ld_wait();
@@ -243,7 +281,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + out_row * args.ldo + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 x = dst[j];
+            float4 x = kPreloadResid ? resid_pre[chunk_i][j] : dst[j];
             x.x += v[4 * j]; x.y += v[4 * j + 1]; x.z += v[4 * j + 2]; x.w += v[4 * j + 3];
             dst[j] = x;
           }
@@ -335,6 +373,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
+// $WVN_GEMM_BRES: 0/unset = streaming tiles; 1 = weight-resident mode with 192-wide tiles where the
+// slab fits; 2 = weight-resident with 128-wide tiles (deeper activation ring).  Experiment knob.
+int bres_env_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("WVN_GEMM_BRES");
+    mode = e ? atoi(e) : 0;
+    if (mode < 0 || mode > 2) mode = 0;
+  }
+  return mode;
+}
+
 template <int BN, int EPI, int ACT>
 int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -344,12 +394,27 @@ int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
     WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
     attr_set = true;
   }
-  const int num_tiles = (EPI == EPI_MLP_HEAD) ? (a.M + BM - 1) / BM : ((a.M + BM - 1) / BM) * (a.N / BN);
+  const int num_m = (a.M + BM - 1) / BM, num_n = a.N / BN;
+  const int num_tiles = (EPI == EPI_MLP_HEAD) ? num_m : num_m * num_n;
   int grid = sm_count();
   if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
   if (grid > num_tiles) grid = num_tiles;
+  GemmArgs launch_args = a;
+  launch_args.b_resident = 0;
+  uint32_t smem_bytes = Cfg::kSmemBytes;
+  if (EPI != EPI_MLP_HEAD && (a.allow_b_resident || bres_env_mode() > 0)) {
+    const int slab = (a.K / BK) * static_cast<int>(Cfg::kBBytes);
+    const int a_stages = std::min<int>(8, (kMaxSmemBytes - kFixedSmemBytes - slab) / static_cast<int>(Cfg::kABytes));
+    const int per_n = grid / num_n;
+    if (a_stages >= 3 && per_n >= 1 && num_m >= 2 * per_n) {
+      launch_args.b_resident = 1;
+      launch_args.a_stages = a_stages;
+      grid = per_n * num_n;
+      smem_bytes = static_cast<uint32_t>(slab + a_stages * static_cast<int>(Cfg::kABytes) + kFixedSmemBytes);
+    }
+  }
   prof_begin(PROF_GEMM, stream);
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, a);
+  kern<<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, launch_args);
   prof_end(PROF_GEMM, stream);
   WVN_CHECK_LAUNCH("gemm_bf16_kernel");
   return WVN_OK;
@@ -399,8 +464,11 @@ int gemm_bf16(const GemmArgs& a, const void* A, long long lda, const void* W, in
   if (block_n == 0) {
     block_n = pick_block_n(a.N);
     // prefer a 192-wide tile whose [192, K] weight slab can stay resident in shared memory
-    if (a.allow_b_resident && a.epi != EPI_MLP_HEAD && a.N % 192 == 0 && (a.K / BK) * 192 * 128 + 3 * 16384 + 2048 <= kMaxSmemBytes)
+    const int mode = a.allow_b_resident ? std::max(1, bres_env_mode()) : bres_env_mode();
+    if (mode == 1 && a.epi != EPI_MLP_HEAD && a.N % 192 == 0 && (a.K / BK) * 192 * 128 + 3 * 16384 + kFixedSmemBytes <= kMaxSmemBytes)
       block_n = 192;
+    if (mode == 2 && a.epi != EPI_MLP_HEAD && a.N % 128 == 0 && (a.K / BK) * 128 * 128 + 3 * 16384 + kFixedSmemBytes <= kMaxSmemBytes)
+      block_n = 128;
   }
   WVN_REQUIRE(block_n == 64 || block_n == 128 || block_n == 192 || block_n == 224 || block_n == 256,
               "gemm: bad block_n %d", block_n);

@@ -299,25 +299,28 @@ token_gram_kernel(const __nv_bfloat16* __restrict__ tok, float* __restrict__ gra
 
 // Weight-only constants of the fused head, from the flat fp32 state-dict parameters (bf16-rounded R,
 // to match the U = tokens @ R columns the tensor core produces from bf16 operands).
-__global__ void pixel_head_consts_kernel(const float* __restrict__ p, MlpOffsets o, int dim, PixelHeadConsts* out) {
-  const int j = threadIdx.x;  // 0..31
-  auto R = [&](int d, int k) { return __bfloat162float(__float2bfloat16_rn(p[o.w3 + static_cast<long long>(1 + d) * kH2 + k])); };
-  if (j < kH2) {
-    out->b2[j] = p[o.b2 + j];
-    out->w0[j] = __bfloat162float(__float2bfloat16_rn(p[o.w3 + j]));  // row 0 of layers.4.weight (bf16 like the GEMM path)
-    float tv = 0.f;
-    for (int d = 0; d < dim; ++d) tv = fmaf(R(d, j), p[o.b3 + 1 + d], tv);
-    out->tv[j] = 2.f * tv;
-    for (int k = 0; k < kH2; ++k) {
-      float m = 0.f;
-      for (int d = 0; d < dim; ++d) m = fmaf(R(d, j), R(d, k), m);
-      out->m[j * kH2 + k] = (k == j) ? m : (k > j ? 2.f * m : 0.f);
-    }
+// One block of 32 x 32 threads: thread (j, k) owns M[j][k]; row 0 also produces tv / b2 / w0.
+__global__ void __launch_bounds__(1024)
+pixel_head_consts_kernel(const float* __restrict__ p, MlpOffsets o, int dim, PixelHeadConsts* out) {
+  const int k = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const float* w3 = p + o.w3 + kH2;  // rows 1.. of layers.4.weight: R[d][*]
+  float m = 0.f, tv = 0.f, cc = 0.f;
+  for (int d = 0; d < dim; ++d) {
+    const float rj = __bfloat162float(__float2bfloat16_rn(w3[static_cast<long long>(d) * kH2 + j]));
+    const float rk = __bfloat162float(__float2bfloat16_rn(w3[static_cast<long long>(d) * kH2 + k]));
+    const float c = p[o.b3 + 1 + d];
+    m = fmaf(rj, rk, m);
+    if (k == 0) tv = fmaf(rj, c, tv);
+    if (threadIdx.x == 0) cc = fmaf(c, c, cc);
   }
-  if (j == 0) {
+  out->m[j * kH2 + k] = (k == j) ? m : (k > j ? 2.f * m : 0.f);
+  if (k == 0) {
+    out->tv[j] = 2.f * tv;
+    out->b2[j] = p[o.b2 + j];
+    out->w0[j] = __bfloat162float(__float2bfloat16_rn(p[o.w3 + j]));  // row 0 (bf16 like the GEMM path)
+  }
+  if (threadIdx.x == 0) {
     out->b0 = p[o.b3];
-    float cc = 0.f;
-    for (int d = 0; d < dim; ++d) cc = fmaf(p[o.b3 + 1 + d], p[o.b3 + 1 + d], cc);
     out->cc = cc;
   }
 }
@@ -358,7 +361,7 @@ int pixel_head_pack(const float* params, const MlpShape& s, int dim_p, void* wca
   const MlpOffsets o = mlp_offsets(s);
   pixel_head_pack_kernel<<<128, 256, 0, stream>>>(params, o, s.dim, dim_p, reinterpret_cast<__nv_bfloat16*>(wcat_bf16), bias);
   WVN_CHECK_LAUNCH("pixel_head_pack_kernel");
-  pixel_head_consts_kernel<<<1, 32, 0, stream>>>(params, o, s.dim, consts);
+  pixel_head_consts_kernel<<<1, 1024, 0, stream>>>(params, o, s.dim, consts);
   WVN_CHECK_LAUNCH("pixel_head_consts_kernel");
   return WVN_OK;
 }

@@ -79,8 +79,8 @@ class StegoInterface:
             self._tokens = vit.forward(img)
             head = vit.stego_head(B)
         S = self._cfg.input_size
-        cl = ops.logits_argmax(head, HEAD_CLUSTER_COL, self._n_clusters, B, npad, g, g, S, S)
-        li = ops.logits_argmax(head, HEAD_LINEAR_COL, self._n_classes, B, npad, g, g, S, S)
+        cl, li = ops.logits_argmax(head, HEAD_CLUSTER_COL, self._n_clusters, B, npad, g, g, S, S,
+                                   col0_b=HEAD_LINEAR_COL, classes_b=self._n_classes)
         code = head.view(B, npad, -1)[:, 1 : 1 + g * g, HEAD_CODE_COL : HEAD_CODE_COL + self._code_dim].contiguous()
         self._code_tokens = code  # (B, P, 90) at patch resolution — what the fused consumers use
         self._code = None         # dense (B,90,H,H) only on demand (property `features`)

@@ -58,11 +58,14 @@ def upsample_dense(tokens, gh, gw, out_h, out_w):
     return out
 
 
-def logits_argmax(logits, col0, classes, batch, npad, gh, gw, out_h, out_w):
+def logits_argmax(logits, col0, classes, batch, npad, gh, gw, out_h, out_w, col0_b=0, classes_b=0):
+    """Per-pixel argmax of bilinearly (align_corners=False) upsampled class logits.  With a second
+    column range the two segmentations come out of one pass: returns seg or (seg, seg_b)."""
     seg = torch.empty(batch, out_h, out_w, device=logits.device, dtype=torch.int64)
-    check(lib().wvn_logits_argmax(ptr(logits), logits.stride(0), col0, classes, batch, npad, gh, gw, out_h, out_w,
-                                  ptr(seg), stream()))
-    return seg
+    seg_b = torch.empty_like(seg) if classes_b > 0 else None
+    check(lib().wvn_logits_argmax(ptr(logits), logits.stride(0), col0, classes, col0_b, classes_b, batch, npad, gh, gw,
+                                  out_h, out_w, ptr(seg), ptr(seg_b), stream()))
+    return seg if seg_b is None else (seg, seg_b)
 
 
 def segment_reduce(seg, smax, tokens=None, grid=None, want_centers=True, want_edges=True, max_edges=None):
