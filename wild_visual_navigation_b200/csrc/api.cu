@@ -1,6 +1,9 @@
 // wvn-b200: the C ABI (include/wvn_b200.h) — handles, composite forward passes, primitives.
 #include <cuda_bf16.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <map>
 #include <string>
 #include <vector>
@@ -140,7 +143,24 @@ int wvn_attention_bf16(const void* q, const void* k, const void* vt, void* out, 
   a.batch = batch; a.heads = heads; a.npad = npad; a.n_valid = n_valid;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.out = out; a.ldo = static_cast<long long>(heads) * 64;
-  return attention_bf16(a, q, k, vt, S(stream));
+  static long long* timing_buf = nullptr;  // $WVN_ATTN_TIMING=1: phase cycle counters, printed after each call
+  static int timing_on = -1;
+  if (timing_on < 0) {
+    const char* e = getenv("WVN_ATTN_TIMING");
+    timing_on = (e && e[0] == '1') ? 1 : 0;
+    if (timing_on) cudaMallocManaged(&timing_buf, 16 * sizeof(long long));
+  }
+  a.timing = timing_on ? timing_buf : nullptr;
+  const int rc = attention_bf16(a, q, k, vt, S(stream));
+  if (timing_on && rc == 0) {
+    cudaStreamSynchronize(S(stream));
+    const int nkv = npad / 128;
+    fprintf(stderr, "[attn timing, cycles per KV tile] softmax: wait_s %lld  ldtm %lld  math %lld  wait_pv %lld  store+fence %lld | "
+            "mma: issue_qk(+waits) %lld  wait_p %lld  wait_v+issue_pv %lld  loop %lld\n",
+            timing_buf[0] / nkv, timing_buf[1] / nkv, timing_buf[2] / nkv, timing_buf[3] / nkv, timing_buf[4] / nkv,
+            timing_buf[8] / nkv, timing_buf[9] / nkv, timing_buf[10] / nkv, timing_buf[11] / nkv);
+  }
+  return rc;
 }
 
 int wvn_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int dim,

@@ -12,6 +12,7 @@ struct AttnArgs {
   float scale_log2 = 0.f;  // head_dim^-0.5 * log2(e)
   void* out = nullptr;     // [batch, npad, ldo] bf16, head h occupies columns [64h, 64h+64)
   long long ldo = 0;
+  long long* timing = nullptr;  // debug: 16 cycle counters of block (0,0) (see scripts/bench_attention.py)
 };
 
 // q, k: [batch*heads, npad, 64] bf16; vt: [batch*heads, 64, npad] bf16.

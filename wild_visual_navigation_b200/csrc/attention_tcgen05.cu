@@ -14,8 +14,14 @@
 // the tensor core works on one CTA's MMAs while the other CTA is in its softmax phase.
 //   warp 0    : TMEM alloc, then TMA producer (Q once; K / V^T tiles, 2 stages each)
 //   warp 1    : MMA issuer  (S = Q K^T : 4 x UMMA 128x128x16;  O += P V : 8 x UMMA 128x64x16)
-//   warps 2-5 : softmax (1 thread = 1 query row): tcgen05.ld S, online softmax with lazy
-//               rescaling, P -> bf16 -> swizzled smem, final O / l epilogue.
+//   warps 2-5 : softmax (1 thread = 1 query row): one tcgen05.ld pass puts the 128 scores of the
+//               row in registers, FMNMX3 row max, lazy rescaling (FA4-style), exp2 on MUFU with an
+//               optional share on the FMA pipe (packed FFMA2 polynomial), P -> bf16 -> swizzled smem,
+//               final O / l epilogue.
+// Measured phase budget per KV tile (clock64, round 1): MUFU issue (1024 clk/warp) is the floor of
+// the softmax phase; the per-tile code path is therefore kept free of mask arithmetic for the 24
+// unmasked tiles (the padded last tile runs a separate, masked instantiation — written as separate
+// template instances because the compiler if-converts a runtime masked/unmasked branch into selects).
 #include <stdlib.h>
 
 #include "attention.h"
@@ -44,9 +50,7 @@ constexpr uint32_t kSmemBytes = kOffBar + 256;
 constexpr uint32_t kTmemCols = 256;  // S: [0,128)  O: [128,192)
 constexpr uint32_t kColS = 0;
 constexpr uint32_t kColO = 128;
-constexpr uint32_t kColMail = 192;  // 6 mailbox columns: [parity 0/1][half 0/1] row maxima, then [half] row sums
 constexpr float kRescaleThreshold = 8.0f;  // in log2 units (FA4-style lazy rescale)
-constexpr int kDefaultSplit = 1;
 constexpr int kDefaultPoly = 0;            // software-exp2 share: pairs out of every 4 pairs (see poly_exp2_pair)
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -81,8 +85,8 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 }
 
 // exp2 on the FMA/ALU pipes (Cody-Waite + degree-3 minimax, rel. err 7.5e-5 — well inside the bf16
-// rounding of P): the MUFU unit (16 ex2/clk/SM) is the binding resource of the softmax phase, so
-// POLY of every 4 element PAIRS are evaluated here instead (FA4-style software exp2 offload).
+// rounding of P): POLY of every 4 element PAIRS are evaluated here instead of on the MUFU unit
+// (16 ex2/clk/SM), FA4-style.
 __device__ __forceinline__ void poly_exp2_pair(uint64_t x2, float& e0, float& e1) {
   float x0, x1;
   unpack2(x2, x0, x1);
@@ -100,16 +104,148 @@ __device__ __forceinline__ void poly_exp2_pair(uint64_t x2, float& e0, float& e1
   e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
-__device__ __forceinline__ float masked_exp(float s, float sl2, float mb, int col, int valid) {
-  return (col < valid) ? fast_exp2(fmaf(s, sl2, -mb)) : 0.f;
+// Per-thread softmax state and the shared-memory / tensor-memory handles one row needs.
+struct SoftmaxCtx {
+  uint32_t tmem_s, tmem_o;
+  uint8_t* p_row;
+  int sw;
+  float sl2;
+  uint64_t *s_full, *s_free, *p_full, *pv_done;
+  float m_ref, l;
+};
+
+// One KV tile of the online softmax for one query row.  MASKED handles the padded last tile
+// (keys >= valid are excluded); the unmasked instantiation carries no mask arithmetic at all.
+template <int POLY, bool MASKED>
+__device__ __forceinline__ void softmax_tile(SoftmaxCtx& c, int j, int valid, long long* tph, bool timing,
+                                             long long& tprev) {
+#ifdef WVN_ATTN_TIMING
+#define WVN_TPH(i) if (timing) { const long long tn = clock64(); tph[i] += tn - tprev; tprev = tn; }
+#else
+#define WVN_TPH(i)
+#endif
+  mbar_wait(c.s_full, j & 1);
+  tc_fence_after();
+  WVN_TPH(0)
+  uint32_t sr[4][32];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tmem_ld32(c.tmem_s + q * 32, sr[q]);
+  tmem_ld_wait();
+  tc_fence_before();
+  mbar_arrive(c.s_free);  // S(j) is in registers: QK^T(j+1) may overwrite it while we do the exps
+  WVN_TPH(1)
+
+  float mx;
+  if (!MASKED) {
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // FMNMX3 chains
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      m0 = max3(m0, __uint_as_float(sr[0][i]), __uint_as_float(sr[0][i + 1]));
+      m1 = max3(m1, __uint_as_float(sr[1][i]), __uint_as_float(sr[1][i + 1]));
+      m2 = max3(m2, __uint_as_float(sr[2][i]), __uint_as_float(sr[2][i + 1]));
+      m3 = max3(m3, __uint_as_float(sr[3][i]), __uint_as_float(sr[3][i + 1]));
+    }
+    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  } else {
+    mx = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (q * 32 + i < valid) ? __uint_as_float(sr[q][i]) : -INFINITY);
+  }
+
+  // ---- reference-max update (lazy: only rescale O when the max grew by > 2^8)
+  bool waited_pv = false;
+  if (j == 0) {
+    c.m_ref = mx;
+  } else {
+    const float m_new = fmaxf(c.m_ref, mx);
+    const bool need = (m_new - c.m_ref) * c.sl2 > kRescaleThreshold;
+    if (__any_sync(0xffffffffu, need)) {
+      mbar_wait(c.pv_done, (j - 1) & 1);  // O must be quiescent
+      waited_pv = true;
+      tc_fence_after();
+      const float alpha = need ? fast_exp2((c.m_ref - m_new) * c.sl2) : 1.f;
+      if (need) c.m_ref = m_new;
+      c.l *= alpha;
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        uint32_t r[32];
+        tmem_ld32(c.tmem_o + q * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+        tmem_st32(c.tmem_o + q * 32, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+    }
+  }
+
+  // ---- P = exp2((s - m_ref) * sl2), packed to bf16 in place in the score registers; row sum
+  const float mb = c.m_ref * c.sl2;
+  if (!MASKED) {
+    const uint64_t sl2_2 = pack2(c.sl2, c.sl2), nmb2 = pack2(-mb, -mb);
+    uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const uint64_t x2 = fma2(pack2(__uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1])), sl2_2, nmb2);
+        float e0, e1;
+        if (POLY == 9) {  // timing experiment only: no exponentials at all (results are wrong)
+          unpack2(x2, e0, e1);
+        } else if (((i >> 1) & 3) < POLY) {
+          poly_exp2_pair(x2, e0, e1);
+        } else {
+          float x0, x1;
+          unpack2(x2, x0, x1);
+          e0 = fast_exp2(x0);
+          e1 = fast_exp2(x1);
+        }
+        if ((i >> 1) & 1) lb = add2(lb, pack2(e0, e1)); else la = add2(la, pack2(e0, e1));
+        sr[q][i >> 1] = pack_bf16x2(e0, e1);  // packed bf16 pairs overwrite the consumed scores
+      }
+    }
+    float s0, s1;
+    unpack2(add2(la, lb), s0, s1);
+    c.l += s0 + s1;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const int col = q * 32 + i;
+        const float e0 = (col < valid) ? fast_exp2(fmaf(__uint_as_float(sr[q][i]), c.sl2, -mb)) : 0.f;
+        const float e1 = (col + 1 < valid) ? fast_exp2(fmaf(__uint_as_float(sr[q][i + 1]), c.sl2, -mb)) : 0.f;
+        c.l += e0 + e1;
+        sr[q][i >> 1] = pack_bf16x2(e0, e1);
+      }
+    }
+  }
+  WVN_TPH(2)
+
+  if (j > 0 && !waited_pv) mbar_wait(c.pv_done, (j - 1) & 1);  // P buffer free again (PV(j-1) retired)
+  WVN_TPH(3)
+  // ---- P -> swizzled smem: 32 columns = 4 x 16-byte chunks of K-block (q >> 1), chunk (q & 1) * 4 + t
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint8_t* blk = c.p_row + (q >> 1) * (kPBytes / 2);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int chunk = ((q & 1) * 4 + t) ^ c.sw;
+      *reinterpret_cast<uint4*>(blk + chunk * 16) =
+          make_uint4(sr[q][4 * t + 0], sr[q][4 * t + 1], sr[q][4 * t + 2], sr[q][4 * t + 3]);
+    }
+  }
+  fence_proxy_async_smem();   // P(j) visible to the tensor core (async proxy)
+  mbar_arrive(c.p_full);
+  WVN_TPH(4)
+#undef WVN_TPH
 }
 
-// SPLIT = threads per query row in the softmax phase.  SPLIT == 2 gives each row to two threads of
-// different warps (64 key columns each): twice the softmax warps per SM to hide the TMEM-load /
-// MUFU / barrier latencies, half the registers per thread; the two halves agree on the reference
-// max through a one-column mailbox in tensor memory (shared memory is full at 2 CTAs/SM).
-template <int POLY, int SPLIT>
-__global__ void __launch_bounds__(64 + 128 * SPLIT, 2)
+template <int POLY>
+__global__ void __launch_bounds__(kThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_vt, const AttnArgs args) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -144,8 +280,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128 * SPLIT);
-    mbar_init(p_full, 128 * SPLIT);
+    mbar_init(s_free, 128);
+    mbar_init(p_full, 128);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -198,13 +334,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         umma_commit(s_full);
       };
 
+#ifdef WVN_ATTN_TIMING
+      const bool timing = args.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+      long long tm[4] = {0, 0, 0, 0}, tprev = timing ? clock64() : 0;
+#else
+      constexpr bool timing = false;
+      long long* tm = nullptr;
+#endif
+#ifdef WVN_ATTN_TIMING
+#define WVN_TM(i) if (timing) { const long long tn = clock64(); tm[i] += tn - tprev; tprev = tn; }
+#else
+#define WVN_TM(i)
+#endif
       mbar_wait(q_full, 0);
       issue_qk(0);
       for (int j = 0; j < nkv; ++j) {
+        WVN_TM(3)
         if (j + 1 < nkv) issue_qk(j + 1);  // overlaps softmax(j)'s tail and P(j) hand-off
+        WVN_TM(0)
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(p_full, j & 1);
+        WVN_TM(1)
         mbar_wait(&v_full[st], ph);
         tc_fence_after();
         const uint32_t p_addr = smem_u32(smem + kOffP);
@@ -217,316 +368,61 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         umma_commit(&v_empty[st]);
         umma_commit(pv_done);
+        WVN_TM(2)
       }
-    }
-  } else if (SPLIT == 2) {
-    // -------------------------------------------------------------- softmax, two threads per row
-    const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;       // which 64 key columns of every tile (= P's K-block)
-    const int row = quarter * 32 + lane;    // row inside the query tile == TMEM lane
-    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tmem_s = tmem_base + lane_base + kColS + half * 64;
-    const uint32_t tmem_o = tmem_base + lane_base + kColO + half * 32;
-    const uint32_t tmem_mail = tmem_base + lane_base + kColMail;  // [parity][half] mailbox columns
-    uint8_t* p_row = smem + kOffP + half * (kPBytes / 2) + row * 128;
-    const int sw = row & 7;
-    const float sl2 = args.scale_log2;
-    float m_ref = -INFINITY, l = 0.f;
-
-    for (int j = 0; j < nkv; ++j) {
-      const int valid = args.n_valid - j * kTileKV - half * 64;  // valid columns of this half
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      uint32_t sr[2][32];
-      tmem_ld32(tmem_s, sr[0]);
-      tmem_ld32(tmem_s + 32, sr[1]);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_free);
-
-      const bool masked = valid < 64;
-      float mx;
-      if (!masked) {
-        float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          m0 = max3(m0, __uint_as_float(sr[0][i]), __uint_as_float(sr[0][i + 1]));
-          m1 = max3(m1, __uint_as_float(sr[1][i]), __uint_as_float(sr[1][i + 1]));
-        }
-        mx = fmaxf(m0, m1);
-      } else {
-        mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < valid) ? __uint_as_float(sr[c][i]) : -INFINITY);
-      }
-      // exchange the half-row maxima with the partner thread (same row, other half) through TMEM
-      const uint32_t mail = tmem_mail + (j & 1) * 2;
-      tmem_st1(mail + half, __float_as_uint(mx));
-      tmem_st_wait();
-      tc_fence_before();
-      named_bar_sync(1 + quarter, 64);
-      tc_fence_after();
-      mx = fmaxf(mx, __uint_as_float(tmem_ld1(mail + (half ^ 1))));
-      tmem_ld_wait();
-
-      bool waited_pv = false;
-      if (j == 0) {
-        m_ref = mx;
-      } else {
-        const float m_new = fmaxf(m_ref, mx);
-        const bool need = (m_new - m_ref) * sl2 > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(pv_done, (j - 1) & 1);
-          waited_pv = true;
-          tc_fence_after();
-          const float alpha = need ? fast_exp2((m_ref - m_new) * sl2) : 1.f;
-          if (need) m_ref = m_new;
-          l *= alpha;
-          uint32_t r[32];
-          tmem_ld32(tmem_o, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st32(tmem_o, r);
-          tmem_st_wait();
-          tc_fence_before();
-        }
-      }
-
-      const float mb = m_ref * sl2;
-      if (!masked) {
-        const uint64_t sl2_2 = pack2(sl2, sl2), nmb2 = pack2(-mb, -mb);
-        uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const uint64_t x2 = fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sl2_2, nmb2);
-            float e0, e1;
-            if (POLY == 9) {  // timing experiment only: no exponentials at all (results are wrong)
-              unpack2(x2, e0, e1);
-            } else if (((i >> 1) & 3) < POLY) {
-              poly_exp2_pair(x2, e0, e1);
-            } else {
-              float x0, x1;
-              unpack2(x2, x0, x1);
-              e0 = fast_exp2(x0);
-              e1 = fast_exp2(x1);
-            }
-            if ((i >> 1) & 1) lb = add2(lb, pack2(e0, e1)); else la = add2(la, pack2(e0, e1));
-            sr[c][i >> 1] = pack_bf16x2(e0, e1);
-          }
-        }
-        float s0, s1;
-        unpack2(add2(la, lb), s0, s1);
-        l += s0 + s1;
-      } else {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float e0 = masked_exp(__uint_as_float(sr[c][i]), sl2, mb, c * 32 + i, valid);
-            const float e1 = masked_exp(__uint_as_float(sr[c][i + 1]), sl2, mb, c * 32 + i + 1, valid);
-            l += e0 + e1;
-            sr[c][i >> 1] = pack_bf16x2(e0, e1);
-          }
-        }
-      }
-
-      if (j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);
-      // this half's 64 columns are exactly K-block `half` of P: 8 swizzled 16-byte chunks
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (c * 4 + q) ^ sw;
-          *reinterpret_cast<uint4*>(p_row + chunk * 16) =
-              make_uint4(sr[c][4 * q + 0], sr[c][4 * q + 1], sr[c][4 * q + 2], sr[c][4 * q + 3]);
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(p_full);
-    }
-
-    // ---- epilogue: combine the two partial row sums, O / l for this half's 32 output columns
-    mbar_wait(pv_done, (nkv - 1) & 1);
-    tc_fence_after();
-    tmem_st1(tmem_mail + 4 + half, __float_as_uint(l));
-    tmem_st_wait();
-    tc_fence_before();
-    named_bar_sync(1 + quarter, 64);
-    tc_fence_after();
-    l += __uint_as_float(tmem_ld1(tmem_mail + 4 + (half ^ 1)));
-    tmem_ld_wait();
-    const float inv_l = 1.f / l;
-    const int b = bh / args.heads;
-    const int h = bh - b * args.heads;
-    const long long q_idx = static_cast<long long>(b) * args.npad + q_tile * kTileQ + row;
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + q_idx * args.ldo + h * kDh + half * 32;
-    uint32_t r[32];
-    tmem_ld32(tmem_o, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float f[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[8 * q + i]) * inv_l;
-      st_global_v4(dst + 8 * q, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                   pack_bf16x2(f[6], f[7]));
+      if (timing)
+        for (int i = 0; i < 4; ++i) args.timing[8 + i] = tm[i];
+#undef WVN_TM
     }
   } else {
     // -------------------------------------------------------------- softmax / correction / epilogue
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;  // row inside the query tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tmem_s = tmem_base + lane_base + kColS;
-    const uint32_t tmem_o = tmem_base + lane_base + kColO;
-    uint8_t* p_row = smem + kOffP + row * 128;
-    const int sw = row & 7;
-    const float sl2 = args.scale_log2;
+    SoftmaxCtx c;
+    c.tmem_s = tmem_base + lane_base + kColS;
+    c.tmem_o = tmem_base + lane_base + kColO;
+    c.p_row = smem + kOffP + row * 128;
+    c.sw = row & 7;
+    c.sl2 = args.scale_log2;
+    c.s_full = s_full; c.s_free = s_free; c.p_full = p_full; c.pv_done = pv_done;
+    c.m_ref = -INFINITY;  // running reference max (raw score units)
+    c.l = 0.f;            // running sum of exp2((s - m_ref) * sl2)
+    // optional phase timing (debug): cycles spent by this thread in each phase, summed over tiles
+#ifdef WVN_ATTN_TIMING
+    const bool timing = args.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
+    long long tph[5] = {0, 0, 0, 0, 0}, tprev = timing ? clock64() : 0;
+#else
+    constexpr bool timing = false;
+    long long* tph = nullptr;
+    long long tprev = 0;
+#endif
 
-    float m_ref = -INFINITY;  // running reference max (raw score units)
-    float l = 0.f;            // running sum of exp2((s - m_ref) * sl2)
-
-    for (int j = 0; j < nkv; ++j) {
-      const int valid = args.n_valid - j * kTileKV;  // columns >= valid are padding tokens
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-
-      // ---- single TMEM pass: the whole 128-wide score row of this thread goes to registers
-      const bool masked = valid < kTileKV;  // only the last KV tile carries padding keys
-      uint32_t sr[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + c * 32, sr[c]);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_free);  // S(j) is in registers: QK^T(j+1) may overwrite it while we do the exps
-
-      float mx;
-      if (!masked) {
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // FMNMX3 chains
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          m0 = max3(m0, __uint_as_float(sr[0][i]), __uint_as_float(sr[0][i + 1]));
-          m1 = max3(m1, __uint_as_float(sr[1][i]), __uint_as_float(sr[1][i + 1]));
-          m2 = max3(m2, __uint_as_float(sr[2][i]), __uint_as_float(sr[2][i + 1]));
-          m3 = max3(m3, __uint_as_float(sr[3][i]), __uint_as_float(sr[3][i + 1]));
-        }
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      } else {
-        mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < valid) ? __uint_as_float(sr[c][i]) : -INFINITY);
-      }
-
-      // ---- reference-max update (lazy: only rescale O when the max grew by > 2^8)
-      bool waited_pv = false;
-      if (j == 0) {
-        m_ref = mx;
-      } else {
-        const float m_new = fmaxf(m_ref, mx);
-        const bool need = (m_new - m_ref) * sl2 > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(pv_done, (j - 1) & 1);  // O must be quiescent
-          waited_pv = true;
-          tc_fence_after();
-          const float alpha = need ? fast_exp2((m_ref - m_new) * sl2) : 1.f;
-          if (need) m_ref = m_new;
-          l *= alpha;
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_o + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st32(tmem_o + c * 32, r);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-        }
-      }
-
-      // ---- P = exp2((s - m_ref) * sl2), in place in the score registers; row sum
-      const float mb = m_ref * sl2;
-      if (!masked) {
-        const uint64_t sl2_2 = pack2(sl2, sl2), nmb2 = pack2(-mb, -mb);
-        uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const uint64_t x2 = fma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sl2_2, nmb2);
-            float e0, e1;
-            if (POLY == 9) {  // timing experiment only: no exponentials at all (results are wrong)
-              unpack2(x2, e0, e1);
-            } else if (((i >> 1) & 3) < POLY) {
-              poly_exp2_pair(x2, e0, e1);
-            } else {
-              float x0, x1;
-              unpack2(x2, x0, x1);
-              e0 = fast_exp2(x0);
-              e1 = fast_exp2(x1);
-            }
-            if ((i >> 1) & 1) lb = add2(lb, pack2(e0, e1)); else la = add2(la, pack2(e0, e1));
-            sr[c][i >> 1] = pack_bf16x2(e0, e1);  // packed bf16 pairs overwrite the consumed scores
-          }
-        }
-        float s0, s1;
-        unpack2(add2(la, lb), s0, s1);
-        l += s0 + s1;
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float e0 = masked_exp(__uint_as_float(sr[c][i]), sl2, mb, c * 32 + i, valid);
-            const float e1 = masked_exp(__uint_as_float(sr[c][i + 1]), sl2, mb, c * 32 + i + 1, valid);
-            l += e0 + e1;
-            sr[c][i >> 1] = pack_bf16x2(e0, e1);
-          }
-        }
-      }
-
-      if (j > 0 && !waited_pv) mbar_wait(pv_done, (j - 1) & 1);  // P buffer free again (PV(j-1) retired)
-      // ---- P -> swizzled smem: 32 columns = 4 x 16-byte chunks of K-block (c >> 1), chunk (c & 1) * 4 + q
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint8_t* blk = p_row + (c >> 1) * (kPBytes / 2);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 1) * 4 + q) ^ sw;
-          *reinterpret_cast<uint4*>(blk + chunk * 16) =
-              make_uint4(sr[c][4 * q + 0], sr[c][4 * q + 1], sr[c][4 * q + 2], sr[c][4 * q + 3]);
-        }
-      }
-      fence_proxy_async_smem();   // P(j) visible to the tensor core (async proxy)
-      mbar_arrive(p_full);
-    }
+    for (int j = 0; j < nkv - 1; ++j) softmax_tile<POLY, false>(c, j, kTileKV, tph, timing, tprev);
+    softmax_tile<(POLY == 9 ? 9 : 0), true>(c, nkv - 1, args.n_valid - (nkv - 1) * kTileKV, tph, timing, tprev);
+    if (timing)
+      for (int i = 0; i < 5; ++i) args.timing[i] = tph[i];
 
     // ---- epilogue: O / l -> bf16 -> out[b, q, h*64 + d]
     mbar_wait(pv_done, (nkv - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.f / l;
+    const float inv_l = 1.f / c.l;
     const int b = bh / args.heads;
     const int h = bh - b * args.heads;
     const long long q_idx = static_cast<long long>(b) * args.npad + q_tile * kTileQ + row;
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + q_idx * args.ldo + h * kDh;
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    for (int q = 0; q < 2; ++q) {
       uint32_t r[32];
-      tmem_ld32(tmem_o + c * 32, r);
+      tmem_ld32(c.tmem_o + q * 32, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int t = 0; t < 4; ++t) {
         float f[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[8 * q + i]) * inv_l;
-        st_global_v4(dst + c * 32 + 8 * q, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[8 * t + i]) * inv_l;
+        st_global_v4(dst + q * 32 + 8 * t, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                      pack_bf16x2(f[6], f[7]));
       }
     }
@@ -552,40 +448,27 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
   WVN_PROPAGATE(make_tmap_bf16_2d(&tq, q, kDh, bh * a.npad, kDh * 2, 64, kTileQ));
   WVN_PROPAGATE(make_tmap_bf16_2d(&tk, k, kDh, bh * a.npad, kDh * 2, 64, kTileKV));
   WVN_PROPAGATE(make_tmap_bf16_2d(&tv, vt, a.npad, bh * kDh, static_cast<uint64_t>(a.npad) * 2, 64, kDh));
-  // fraction (in quarters) of the exponentials evaluated on the FMA pipe; tuned on B200, overridable
+  // share (in quarters) of the exponentials evaluated on the FMA pipe; tuned on B200, overridable
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("WVN_ATTN_POLY");
     poly = e ? atoi(e) : kDefaultPoly;
     if ((poly < 0 || poly > 3) && poly != 9) poly = kDefaultPoly;
   }
-  static int split = -1;
-  if (split < 0) {
-    const char* e = getenv("WVN_ATTN_SPLIT");
-    split = e ? atoi(e) : kDefaultSplit;
-    if (split != 1 && split != 2) split = kDefaultSplit;
-  }
   dim3 grid(a.npad / kTileQ, static_cast<unsigned>(bh));
-  auto launch = [&](auto kern, int threads) -> int {
+  auto launch = [&](auto kern) -> int {
     WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     prof_begin(PROF_ATTENTION, stream);
-    kern<<<grid, threads, kSmemBytes, stream>>>(tq, tk, tv, a);
+    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, a);
     prof_end(PROF_ATTENTION, stream);
     return WVN_OK;
   };
-  if (split == 2) {
-    switch (poly) {
-      case 0: WVN_PROPAGATE(launch(attention_kernel<0, 2>, 320)); break;
-      case 1: WVN_PROPAGATE(launch(attention_kernel<1, 2>, 320)); break;
-      default: WVN_PROPAGATE(launch(attention_kernel<2, 2>, 320)); break;
-    }
-  } else {
-    switch (poly) {
-      case 0: WVN_PROPAGATE(launch(attention_kernel<0, 1>, 192)); break;
-      case 1: WVN_PROPAGATE(launch(attention_kernel<1, 1>, 192)); break;
-      case 9: WVN_PROPAGATE(launch(attention_kernel<9, 1>, 192)); break;
-      default: WVN_PROPAGATE(launch(attention_kernel<2, 1>, 192)); break;
-    }
+  switch (poly) {
+    case 0: WVN_PROPAGATE(launch(attention_kernel<0>)); break;
+    case 1: WVN_PROPAGATE(launch(attention_kernel<1>)); break;
+    case 2: WVN_PROPAGATE(launch(attention_kernel<2>)); break;
+    case 3: WVN_PROPAGATE(launch(attention_kernel<3>)); break;
+    default: WVN_PROPAGATE(launch(attention_kernel<9>)); break;
   }
   WVN_CHECK_LAUNCH("attention_kernel");
   return WVN_OK;
