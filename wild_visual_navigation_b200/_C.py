@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_longlo
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwvn_b200.so")
+LIB_PATH = os.environ.get("WVN_B200_LIB", os.path.join(_HERE, "libwvn_b200.so"))  # override: instrumented builds
 
 
 class WvnError(RuntimeError):

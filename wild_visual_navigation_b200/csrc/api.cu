@@ -134,7 +134,21 @@ int wvn_gemm_bf16(const void* a, long long lda, const void* w, const float* bias
   g.epi = out_kind == 0 ? EPI_BF16 : (out_kind == 1 ? EPI_F32 : EPI_RESID_F32);
   WVN_REQUIRE(out_kind >= 0 && out_kind <= 2, "wvn_gemm_bf16: out_kind %d", out_kind);
   g.act = act; g.bias = bias; g.out = out; g.ldo = ldo;
+#ifdef WVN_GEMM_TIMING
+  static long long* tbuf = nullptr;
+  if (!tbuf) cudaMallocManaged(&tbuf, 8 * sizeof(long long));
+  for (int i = 0; i < 8; ++i) tbuf[i] = 0;
+  g.timing = tbuf;
+  const int rc = gemm_bf16(g, a, lda, w, block_n, S(stream));
+  cudaStreamSynchronize(S(stream));
+  const long long nt = tbuf[3] > 0 ? tbuf[3] : 1;
+  fprintf(stderr, "[gemm timing M=%d N=%d K=%d kind=%d act=%d, cycles per tile of CTA 0 (%lld tiles)] mma: wait_acc_empty %lld  "
+          "wait_full(TMA) %lld  issue+commit %lld | epilogue: wait_acc_full %lld  work %lld\n",
+          m, n, k, out_kind, act, nt, tbuf[0] / nt, tbuf[1] / nt, tbuf[2] / nt, tbuf[4] / nt, tbuf[5] / nt);
+  return rc;
+#else
   return gemm_bf16(g, a, lda, w, block_n, S(stream));
+#endif
 }
 
 int wvn_attention_bf16(const void* q, const void* k, const void* vt, void* out, int batch, int heads, int npad,

@@ -50,6 +50,8 @@ struct GemmArgs {
   int allow_b_resident = 0;     // let the launcher pin the weight slab in smem when it fits (measured slower on B200: off)
   int b_resident = 0;           // (set by the launcher)
   int a_stages = 0;             // (set by the launcher)
+  long long* timing = nullptr;  // debug (-DWVN_GEMM_TIMING builds): phase cycle counters of CTA 0
+  int cluster = 1;              // (set by the launcher) thread-block cluster size along M for weight multicast
 };
 
 int pick_block_n(int N);

@@ -30,7 +30,10 @@ constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiThreads = 256;
 constexpr int kMaxSmemBytes = 227 * 1024;
-constexpr int kFixedSmemBytes = 1024 /*barriers + scratch*/ + 1024 /*align slack*/;
+constexpr int kDefaultCluster = 1;  // thread-block cluster size for weight-tile multicast (tuned on B200)
+constexpr int kEpiBufBytes = 4096;                            // one 32-row x 128-byte staging tile
+constexpr int kEpiStageBytes = 8 * 2 * kEpiBufBytes;          // 8 epilogue warps x 2 buffers (TMA-store staging)
+constexpr int kFixedSmemBytes = 1024 /*barriers + scratch*/ + kEpiStageBytes + 1024 /*align slack*/;
 
 // Tile enumeration.  Default: tile ids run n-fastest over the whole (m, n) grid and are
 // dealt round-robin to CTAs (neighbouring CTAs share the A tile through L2).  ROW_OWNER
@@ -44,14 +47,23 @@ template <bool ROW_OWNER>
 struct TileIter {
   int num_m, num_n, m_blk, n_blk, lin, step;
   bool bres;
-  __device__ TileIter(int nm, int nn, bool b_resident) : num_m(nm), num_n(nn), m_blk(0), n_blk(0), lin(0), step(0), bres(b_resident) {
-    if (bres) { n_blk = blockIdx.x % num_n; m_blk = blockIdx.x / num_n; step = gridDim.x / num_n; }
+  int cs, rank, m_grp, num_grp;  // cluster mode: the cs CTAs of a cluster walk (m-group, n) items in lockstep
+  __device__ TileIter(int nm, int nn, bool b_resident, int cluster = 1, int cta_rank = 0)
+      : num_m(nm), num_n(nn), m_blk(0), n_blk(0), lin(0), step(0), bres(b_resident), cs(cluster), rank(cta_rank),
+        m_grp(0), num_grp(0) {
+    if (cs > 1) {
+      num_grp = (num_m + cs - 1) / cs;
+      lin = blockIdx.x / cs; step = gridDim.x / cs;
+      m_grp = lin / num_n; n_blk = lin % num_n; m_blk = m_grp * cs + rank;
+    }
+    else if (bres) { n_blk = blockIdx.x % num_n; m_blk = blockIdx.x / num_n; step = gridDim.x / num_n; }
     else if (ROW_OWNER) { m_blk = blockIdx.x; n_blk = 0; }
     else { lin = blockIdx.x; m_blk = lin / num_n; n_blk = lin % num_n; }
   }
-  __device__ bool valid() const { return m_blk < num_m; }
+  __device__ bool valid() const { return cs > 1 ? m_grp < num_grp : m_blk < num_m; }
   __device__ void next() {
-    if (bres) { m_blk += step; }
+    if (cs > 1) { lin += step; m_grp = lin / num_n; n_blk = lin % num_n; m_blk = m_grp * cs + rank; }
+    else if (bres) { m_blk += step; }
     else if (ROW_OWNER) { if (++n_blk == num_n) { n_blk = 0; m_blk += gridDim.x; } }
     else { lin += gridDim.x; m_blk = lin / num_n; n_blk = lin % num_n; }
   }
@@ -62,7 +74,7 @@ struct GemmCfg {
   static constexpr uint32_t kABytes = BM * BK * 2;
   static constexpr uint32_t kBBytes = BN * BK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;
+  static constexpr int kStagesRaw = (kMaxSmemBytes - kFixedSmemBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kFixedSmemBytes;
@@ -93,6 +105,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int BN, int EPI, int ACT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                  const GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   constexpr int kMaxStages = 8;
@@ -120,7 +133,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int num_n = args.N / BN;
   const int num_k = args.K / BK;
   constexpr bool ROW_OWNER = (EPI == EPI_MLP_HEAD);
+  // cluster mode (cs = 2 or 4 CTAs along M, same n-block): each CTA fetches 1/cs of every weight
+  // k-block and multicasts it to the whole cluster, cutting the L2 -> SM operand traffic that
+  // bounds these GEMMs (A: 16 KB + B: BN*128/cs bytes per CTA per k-block).
+  const int cs = args.cluster > 1 ? args.cluster : 1;
+  const int crank = cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
   float* row_acc = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);  // [128] EPI_MLP_HEAD scratch
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;         // [8 warps][2][4 KB] TMA-store staging
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -129,7 +149,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], cs);  // every CTA of the cluster must have drained the slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -141,6 +161,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts / arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -155,13 +176,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = 0; kb < num_k; ++kb)
           tma_load_2d(&tmap_b, b_full, smem_b + kb * Cfg::kBBytes, kb * BK, n_blk * BN);
       }
-      for (TileIter<ROW_OWNER> it(num_m, num_n, bres); it.valid(); it.next()) {
+      for (TileIter<ROW_OWNER> it(num_m, num_n, bres, cs, crank); it.valid(); it.next()) {
         const int m_blk = it.m_blk, n_blk = it.n_blk;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], bres ? Cfg::kABytes : Cfg::kStageBytes);
           tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * BK, m_blk * BM);
-          if (!bres) tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * BK, n_blk * BN);
+          if (cs > 1) {
+            const int rows = BN / cs;  // this CTA's slice of the weight tile, multicast to the cluster
+            tma_load_2d_mcast(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes + crank * rows * 128, kb * BK,
+                              n_blk * BN + crank * rows, cmask);
+          } else if (!bres) {
+            tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -175,13 +202,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       if (bres) mbar_wait(b_full, 0);
-      for (TileIter<ROW_OWNER> it(num_m, num_n, bres); it.valid(); it.next()) {
+#ifdef WVN_GEMM_TIMING
+      const bool timing = args.timing != nullptr && blockIdx.x == 0;
+      long long tm[4] = {0, 0, 0, 0}, tprev = clock64(), ntiles = 0;
+#define WVN_TM(i) if (timing) { const long long tn = clock64(); tm[i] += tn - tprev; tprev = tn; }
+#else
+#define WVN_TM(i)
+#endif
+      for (TileIter<ROW_OWNER> it(num_m, num_n, bres, cs, crank); it.valid(); it.next()) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        WVN_TM(0)
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          WVN_TM(1)
           const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
           const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + (bres ? kb : stage) * Cfg::kBBytes));
 #pragma unroll
@@ -189,12 +225,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in (addr>>4) units
             umma_bf16_ss(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire (in cluster mode: tell every peer's producer)
+          if (cs > 1) umma_commit_mcast(&empty_bar[stage], cmask); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          WVN_TM(2)
         }
         umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#ifdef WVN_GEMM_TIMING
+        ++ntiles;
+#endif
       }
+#ifdef WVN_GEMM_TIMING
+      if (timing) { for (int i = 0; i < 3; ++i) args.timing[i] = tm[i]; args.timing[3] = ntiles; }
+#endif
+#undef WVN_TM
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------------ epilogue
@@ -204,31 +249,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     float head_partial = 0.f;
+    uint32_t stg_cnt = 0;  // staging-buffer parity of this warp's TMA stores
     if (EPI == EPI_MLP_HEAD && half == 0) row_acc[row_in_tile] = 0.f;
     if (EPI == EPI_MLP_HEAD) asm volatile("bar.sync 1, 256;" ::: "memory");
-    for (TileIter<ROW_OWNER> it(num_m, num_n, bres); it.valid(); it.next()) {
+    for (TileIter<ROW_OWNER> it(num_m, num_n, bres, cs, crank); it.valid(); it.next()) {
       const int m_blk = it.m_blk, n_blk = it.n_blk;
       const int row = m_blk * BM + row_in_tile;
       const bool row_ok = row < args.M;
-      // Residual epilogue: fetch this thread's slice of the residual row BEFORE waiting for the
-      // accumulator, so the global-load latency hides behind the tile's MMA time.
-      constexpr bool kPreloadResid = (EPI == EPI_RESID_F32) && (BN <= 192);
       constexpr int kChunksPerThread = (BN + 63) / 64;
-      float4 resid_pre[kPreloadResid ? kChunksPerThread : 1][8];
-      if (kPreloadResid && row_ok) {
-#pragma unroll
-        for (int ci = 0; ci < kChunksPerThread; ++ci) {
-          const int c0 = half * 32 + 64 * ci;
-          if (c0 < BN) {
-            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(args.out) +
-                                                               static_cast<long long>(row) * args.ldo + n_blk * BN + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) resid_pre[ci][j] = src[j];
-          }
-        }
-      }
+#ifdef WVN_GEMM_TIMING
+      const bool etiming = args.timing != nullptr && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32;
+      long long et0 = clock64();
+#endif
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
+#ifdef WVN_GEMM_TIMING
+      long long et1 = clock64();
+#endif
 
       // Per-row destination bookkeeping
       long long out_row = row;
@@ -265,26 +302,51 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ACT);
         }
-        if (!row_ok) {
-          // out-of-range tail row: nothing to store (loads above stay warp-convergent)
-        } else if (EPI == EPI_BF16) {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + out_row * args.ldo + col0;
+        // ---- stores through the TMA: the 32x32 chunk of this warp is staged in shared memory in the
+        // swizzled layout the tensor map expects, then one lane issues a bulk tensor store (or, for the
+        // residual stream, a bulk reduce-add: x += acc + bias happens at L2, no residual load at all).
+        // Per-thread row-wise stores were LSU-wavefront-bound (every 16-byte piece of a lane lies in a
+        // different 128-byte line): measured 7.6k-19k clk/tile of epilogue against 2.3k clk of MMA.
+        constexpr bool kTmaEpi = (EPI == EPI_BF16 || EPI == EPI_F32 || EPI == EPI_RESID_F32 || EPI == EPI_QKV);
+        bool qkv_is_v = false;
+        if (EPI == EPI_QKV) qkv_is_v = (col0 >= 2 * args.dim);
+        if (kTmaEpi && !qkv_is_v) {
+          uint8_t* buf = epi_stage + ((warp - kEpiWarp0) * 2 + (stg_cnt & 1)) * kEpiBufBytes;
+          if (lane == 0) tma_store_wait_read<1>();  // the store that last read this buffer has drained it
+          __syncwarp();
+          if (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            st_global_v4(dst + 8 * j, pack_bf16x2(v[8 * j + 0], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                         pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-        } else if (EPI == EPI_F32) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + out_row * args.ldo + col0);
+            for (int q = 0; q < 8; ++q)  // 128-byte rows, 128B swizzle: 16-byte chunk q of row r -> q ^ (r & 7)
+              *reinterpret_cast<float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else if (EPI == EPI_RESID_F32) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + out_row * args.ldo + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 x = kPreloadResid ? resid_pre[chunk_i][j] : dst[j];
-            x.x += v[4 * j]; x.y += v[4 * j + 1]; x.z += v[4 * j + 2]; x.w += v[4 * j + 3];
-            dst[j] = x;
+            for (int q = 0; q < 4; ++q)  // 64-byte rows, 64B swizzle: chunk q of row r -> q ^ ((r >> 1) & 3)
+              *reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                             pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
           }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int row_base = m_blk * BM + quarter * 32;
+            if (EPI == EPI_F32 || EPI == EPI_BF16) {
+              tma_store_2d(&tmap_c, buf, col0, row_base);
+            } else if (EPI == EPI_RESID_F32) {
+              tma_reduce_add_2d(&tmap_c, buf, col0, row_base);
+            } else {  // Q / K: [b*h, npad, 64] seen as a 2-D [b*h*npad, 64] tensor
+              const int which = col0 / args.dim;
+              const int within = col0 - which * args.dim;
+              const int fr = row_base / args.npad, tk0 = row_base - fr * args.npad;
+              const int orow = (fr * args.heads + (within >> 6)) * args.npad + tk0;
+              tma_store_2d(which == 0 ? &tmap_c : &tmap_c2, buf, within & 63, orow);
+            }
+            tma_store_commit();
+          }
+          ++stg_cnt;
+        }
+        if (!row_ok) {
+          // out-of-range tail row: no per-row work below (TMA stores clip rows >= M themselves)
         } else if (EPI == EPI_PATCH) {
           const float4* p4 = reinterpret_cast<const float4*>(args.pos + static_cast<long long>(1 + tok) * args.ldo + col0);
           float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + out_row * args.ldo + col0);
@@ -314,32 +376,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           } else if (col0 == args.trav_col) {
             args.trav[row] = 1.f / (1.f + __expf(-v[0]));
           }
-        } else if (EPI == EPI_QKV) {
-          // column -> (q|k|v, head, d); a 32-column chunk never straddles a head (dh = 64)
-          const int which = col0 / args.dim;
-          const int within = col0 - which * args.dim;
-          const int head = within >> 6;
-          const int d0 = within & 63;
-          const long long bh = static_cast<long long>(frame) * args.heads + head;
-          if (which < 2) {
-            __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(which == 0 ? args.q : args.k);
-            __nv_bfloat16* dst = base + (bh * args.npad + tok) * 64 + d0;
+        } else if (EPI == EPI_QKV && qkv_is_v) {
+          // V is stored transposed ([b, h, d, token]) so that P·V consumes it K-major: lanes already run
+          // along tokens, so these direct stores are 64-byte coalesced per instruction.
+          const int within = col0 - 2 * args.dim;
+          const long long bh = static_cast<long long>(frame) * args.heads + (within >> 6);
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.vt) + (bh * 64 + (within & 63)) * args.npad + tok;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              st_global_v4(dst + 8 * j, pack_bf16x2(v[8 * j + 0], v[8 * j + 1]),
-                           pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
-                           pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-          } else {
-            // V is stored transposed ([b, h, d, token]) so that P·V consumes it K-major.
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.vt) + (bh * 64 + d0) * args.npad + tok;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * args.npad] = __float2bfloat16_rn(v[j]);
-          }
+          for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * args.npad] = __float2bfloat16_rn(v[j]);
         }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#ifdef WVN_GEMM_TIMING
+      if (etiming) { args.timing[4] += et1 - et0; args.timing[5] += clock64() - et1; }
+#endif
 
       if (EPI == EPI_MLP_HEAD && n_blk == num_n - 1) {
         // combine the two column-halves of each row, then loss_reco -> confidence
@@ -363,10 +415,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
+    if (lane == 0) tma_store_wait_all<0>();  // all bulk stores of this warp have completed
   }
 
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();  // no CTA may exit while peers can still write its smem / barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -386,7 +440,8 @@ int bres_env_mode() {
 }
 
 template <int BN, int EPI, int ACT>
-int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                const CUtensorMap& tc2, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_bf16_kernel<BN, EPI, ACT>;
   static bool attr_set = false;
@@ -414,34 +469,56 @@ int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
     }
   }
   prof_begin(PROF_GEMM, stream);
-  kern<<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, launch_args);
+  if (a.cluster > 1) {
+    // thread-block cluster along M: grid must be a whole number of clusters
+    const int cs = a.cluster;
+    const int num_items = ((num_m + cs - 1) / cs) * num_n;
+    int clusters = sm_count() / cs;
+    if (clusters > num_items) clusters = num_items;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * cs);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WVN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tc2, launch_args));
+  } else {
+    kern<<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, tc, tc2, launch_args);
+  }
   prof_end(PROF_GEMM, stream);
   WVN_CHECK_LAUNCH("gemm_bf16_kernel");
   return WVN_OK;
 }
 
 template <int BN>
-int dispatch_epi(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t s) {
+int dispatch_epi(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                 const CUtensorMap& tc2, cudaStream_t s) {
   switch (a.epi) {
     case EPI_BF16:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_BF16, ACT_NONE>(a, ta, tb, s);
-      if (a.act == ACT_RELU) return launch_gemm<BN, EPI_BF16, ACT_RELU>(a, ta, tb, s);
-      if (a.act == ACT_GELU) return launch_gemm<BN, EPI_BF16, ACT_GELU>(a, ta, tb, s);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_BF16, ACT_NONE>(a, ta, tb, tc, tc2, s);
+      if (a.act == ACT_RELU) return launch_gemm<BN, EPI_BF16, ACT_RELU>(a, ta, tb, tc, tc2, s);
+      if (a.act == ACT_GELU) return launch_gemm<BN, EPI_BF16, ACT_GELU>(a, ta, tb, tc, tc2, s);
       break;
     case EPI_F32:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_F32, ACT_NONE>(a, ta, tb, s);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_F32, ACT_NONE>(a, ta, tb, tc, tc2, s);
       break;
     case EPI_RESID_F32:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_RESID_F32, ACT_NONE>(a, ta, tb, s);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_RESID_F32, ACT_NONE>(a, ta, tb, tc, tc2, s);
       break;
     case EPI_PATCH:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_PATCH, ACT_NONE>(a, ta, tb, s);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_PATCH, ACT_NONE>(a, ta, tb, tc, tc2, s);
       break;
     case EPI_QKV:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_QKV, ACT_NONE>(a, ta, tb, s);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_QKV, ACT_NONE>(a, ta, tb, tc, tc2, s);
       break;
     case EPI_MLP_HEAD:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_MLP_HEAD, ACT_NONE>(a, ta, tb, s);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_MLP_HEAD, ACT_NONE>(a, ta, tb, tc, tc2, s);
       break;
   }
   return set_error(WVN_ERR_INVALID, "gemm: unsupported epilogue/activation combination (%d, %d)", a.epi, a.act);
@@ -481,15 +558,43 @@ int gemm_bf16(const GemmArgs& a, const void* A, long long lda, const void* W, in
   if (a.epi == EPI_QKV)
     WVN_REQUIRE(a.dim % 64 == 0 && a.N == 3 * a.dim && a.heads * 64 == a.dim && a.npad % 8 == 0,
                 "gemm: bad QKV epilogue geometry (dim=%d heads=%d npad=%d N=%d)", a.dim, a.heads, a.npad, a.N);
+  // Cluster multicast of the weight tile ($WVN_GEMM_CLUSTER = 1 | 2 | 4, default kDefaultCluster): only for
+  // streaming tiles with enough m-blocks to fill the machine, never with the row-owner head epilogue.
+  GemmArgs b = a;
+  static int env_cluster = -1;
+  if (env_cluster < 0) {
+    const char* e = getenv("WVN_GEMM_CLUSTER");
+    env_cluster = e ? atoi(e) : kDefaultCluster;
+    if (env_cluster != 1 && env_cluster != 2 && env_cluster != 4) env_cluster = kDefaultCluster;
+  }
+  const int num_m = (a.M + BM - 1) / BM;
+  b.cluster = 1;
+  if (a.epi != EPI_MLP_HEAD && !a.allow_b_resident && bres_env_mode() == 0 && env_cluster > 1 &&
+      num_m * (a.N / block_n) >= 2 * sm_count() && (block_n / env_cluster) % 8 == 0)
+    b.cluster = env_cluster;
   CUtensorMap ta, tb;
   WVN_PROPAGATE(make_tmap_bf16_2d(&ta, A, a.K, a.M, static_cast<uint64_t>(lda) * 2, BK, BM));
-  WVN_PROPAGATE(make_tmap_bf16_2d(&tb, W, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, block_n));
+  WVN_PROPAGATE(make_tmap_bf16_2d(&tb, W, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, block_n / b.cluster));
+  // output tensor maps for the TMA-store epilogues (32 x 32 boxes; fp32: 128B swizzle, bf16: 64B swizzle)
+  CUtensorMap tc = ta, tc2 = ta;
+  if (a.epi == EPI_F32 || a.epi == EPI_RESID_F32) {
+    WVN_REQUIRE(a.ldo % 4 == 0, "gemm: fp32 output pitch must be a multiple of 4");
+    WVN_PROPAGATE(make_tmap_2d(&tc, a.out, 4, a.N, a.M, static_cast<uint64_t>(a.ldo) * 4, 32, 32, 128));
+  } else if (a.epi == EPI_BF16) {
+    WVN_REQUIRE(a.ldo % 8 == 0, "gemm: bf16 output pitch must be a multiple of 8");
+    WVN_PROPAGATE(make_tmap_2d(&tc, a.out, 2, a.N, a.M, static_cast<uint64_t>(a.ldo) * 2, 32, 32, 64));
+  } else if (a.epi == EPI_QKV) {
+    const uint64_t rows = static_cast<uint64_t>(a.M / a.npad) * a.heads * a.npad;
+    WVN_REQUIRE(a.M % a.npad == 0, "gemm: QKV rows must be whole frames");
+    WVN_PROPAGATE(make_tmap_2d(&tc, a.q, 2, 64, rows, 128, 32, 32, 64));
+    WVN_PROPAGATE(make_tmap_2d(&tc2, a.k, 2, 64, rows, 128, 32, 32, 64));
+  }
   switch (block_n) {
-    case 64: return dispatch_epi<64>(a, ta, tb, stream);
-    case 128: return dispatch_epi<128>(a, ta, tb, stream);
-    case 192: return dispatch_epi<192>(a, ta, tb, stream);
-    case 224: return dispatch_epi<224>(a, ta, tb, stream);
-    case 256: return dispatch_epi<256>(a, ta, tb, stream);
+    case 64: return dispatch_epi<64>(b, ta, tb, tc, tc2, stream);
+    case 128: return dispatch_epi<128>(b, ta, tb, tc, tc2, stream);
+    case 192: return dispatch_epi<192>(b, ta, tb, tc, tc2, stream);
+    case 224: return dispatch_epi<224>(b, ta, tb, tc, tc2, stream);
+    case 256: return dispatch_epi<256>(b, ta, tb, tc, tc2, stream);
   }
   return set_error(WVN_ERR_INVALID, "gemm: unreachable");
 }

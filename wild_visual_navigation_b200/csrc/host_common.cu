@@ -60,6 +60,32 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t inner, uint64
   return WVN_OK;
 }
 
+int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return set_error(WVN_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (elem_bytes != 2 && elem_bytes != 4) return set_error(WVN_ERR_INVALID, "tensor map: element size %d", elem_bytes);
+  if (swizzle_bytes != 0 && box_inner * elem_bytes != static_cast<uint32_t>(swizzle_bytes))
+    return set_error(WVN_ERR_INVALID, "tensor map: inner box (%u B) must equal the swizzle span (%d B)",
+                     box_inner * elem_bytes, swizzle_bytes);
+  if (box_outer > 256 || (reinterpret_cast<uintptr_t>(gptr) & 15) != 0 || (row_stride_bytes & 15) != 0)
+    return set_error(WVN_ERR_INVALID, "tensor map: bad box / alignment (ptr=%p stride=%llu)", gptr,
+                     (unsigned long long)row_stride_bytes);
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(gptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(WVN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu)", (int)r,
+                     (unsigned long long)inner, (unsigned long long)outer);
+  return WVN_OK;
+}
+
 int sm_count() {
   static int n = 0;
   if (n) return n;

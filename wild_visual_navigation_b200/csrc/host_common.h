@@ -53,6 +53,11 @@ const char* last_error();
 int make_tmap_bf16_2d(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t outer,
                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
+// Generic 2D row-major tensor map: elem_bytes in {2 (bf16), 4 (fp32)}; swizzle_bytes in {0, 64, 128}
+// (the inner box must span exactly swizzle_bytes when swizzling).
+int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
+
 int sm_count();
 
 // Kernel-launch counter (every launch of one of this library's kernels) and an optional
