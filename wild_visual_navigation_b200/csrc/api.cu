@@ -343,14 +343,36 @@ int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_
     }
     LayerNormArgs la;
     la.rows = rows; la.dim = D; la.eps = c.ln_eps; la.npad = h->npad; la.n_valid = h->n_valid;
+    // GEMMs / LayerNorms can run over sub-chunks of `sub` frames ($WVN_VIT_SUBCHUNK) to keep xn / hid / x
+    // L2-resident between producer and consumer, while attention always covers the whole chunk.  Measured
+    // on B200 (round 1): sub-chunking LOSES (1631 / 1563 / 1453 / 1253 frames/s at sub = 32 / 16 / 8 / 4) —
+    // the skinny-K GEMMs are bound by the per-SM L2->smem ingest rate, not by DRAM — so the default is off.
+    static int sub_env = -1;
+    if (sub_env < 0) {
+      const char* e = getenv("WVN_VIT_SUBCHUNK");
+      sub_env = e ? atoi(e) : (1 << 30);
+      if (sub_env < 1) sub_env = 1 << 30;
+    }
+    const int sub = std::min(sub_env, nb);
+    __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(h->xn.p);
+    __nv_bfloat16* attn = reinterpret_cast<__nv_bfloat16*>(h->attn.p);
     for (int l = 0; l < c.depth; ++l) {
       const std::string b = "blocks." + std::to_string(l) + ".";
-      WVN_PROPAGATE(layernorm_rows(x, h->wp<float>(b + "norm1.weight"), h->wp<float>(b + "norm1.bias"), h->xn.p, nullptr, la, s));
-      {
+      for (int s0 = 0; s0 < nb; s0 += sub) {
+        const int ns = std::min(sub, nb - s0);
+        const long long roff = static_cast<long long>(s0) * h->npad;
+        LayerNormArgs ls = la;
+        ls.rows = static_cast<long long>(ns) * h->npad;
+        WVN_PROPAGATE(layernorm_rows(x + roff * D, h->wp<float>(b + "norm1.weight"), h->wp<float>(b + "norm1.bias"),
+                                     xn + roff * D, nullptr, ls, s));
         GemmArgs g;
-        g.M = rows; g.N = 3 * D; g.K = D; g.epi = EPI_QKV; g.bias = h->wp<float>(b + "attn.qkv.bias");
-        g.npad = h->npad; g.dim = D; g.heads = c.heads; g.q = h->q.p; g.k = h->k.p; g.vt = h->vt.p;
-        WVN_PROPAGATE(gemm_bf16(g, h->xn.p, D, h->wp<void>(b + "attn.qkv.weight"), 0, s));
+        g.M = ns * h->npad; g.N = 3 * D; g.K = D; g.epi = EPI_QKV; g.bias = h->wp<float>(b + "attn.qkv.bias");
+        g.npad = h->npad; g.dim = D; g.heads = c.heads;
+        const long long hoff = static_cast<long long>(s0) * c.heads * h->npad * 64;  // frames are outermost in q / k / vt
+        g.q = reinterpret_cast<__nv_bfloat16*>(h->q.p) + hoff;
+        g.k = reinterpret_cast<__nv_bfloat16*>(h->k.p) + hoff;
+        g.vt = reinterpret_cast<__nv_bfloat16*>(h->vt.p) + hoff;
+        WVN_PROPAGATE(gemm_bf16(g, xn + roff * D, D, h->wp<void>(b + "attn.qkv.weight"), 0, s));
       }
       {
         AttnArgs a;
@@ -359,24 +381,32 @@ int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_
         a.out = h->attn.p; a.ldo = D;
         WVN_PROPAGATE(attention_bf16(a, h->q.p, h->k.p, h->vt.p, s));
       }
-      {
-        GemmArgs g;
-        g.M = rows; g.N = D; g.K = D; g.epi = EPI_RESID_F32; g.bias = h->wp<float>(b + "attn.proj.bias");
-        g.out = x; g.ldo = D;
-        WVN_PROPAGATE(gemm_bf16(g, h->attn.p, D, h->wp<void>(b + "attn.proj.weight"), 0, s));
-      }
-      WVN_PROPAGATE(layernorm_rows(x, h->wp<float>(b + "norm2.weight"), h->wp<float>(b + "norm2.bias"), h->xn.p, nullptr, la, s));
-      {
-        GemmArgs g;
-        g.M = rows; g.N = c.mlp_dim; g.K = D; g.epi = EPI_BF16; g.act = ACT_GELU;
-        g.bias = h->wp<float>(b + "mlp.fc1.bias"); g.out = h->hid.p; g.ldo = c.mlp_dim;
-        WVN_PROPAGATE(gemm_bf16(g, h->xn.p, D, h->wp<void>(b + "mlp.fc1.weight"), 0, s));
-      }
-      {
-        GemmArgs g;
-        g.M = rows; g.N = D; g.K = c.mlp_dim; g.epi = EPI_RESID_F32; g.bias = h->wp<float>(b + "mlp.fc2.bias");
-        g.out = x; g.ldo = D;
-        WVN_PROPAGATE(gemm_bf16(g, h->hid.p, c.mlp_dim, h->wp<void>(b + "mlp.fc2.weight"), 0, s));
+      for (int s0 = 0; s0 < nb; s0 += sub) {
+        const int ns = std::min(sub, nb - s0);
+        const long long roff = static_cast<long long>(s0) * h->npad;
+        const int srows = ns * h->npad;
+        LayerNormArgs ls = la;
+        ls.rows = srows;
+        {
+          GemmArgs g;
+          g.M = srows; g.N = D; g.K = D; g.epi = EPI_RESID_F32; g.bias = h->wp<float>(b + "attn.proj.bias");
+          g.out = x + roff * D; g.ldo = D;
+          WVN_PROPAGATE(gemm_bf16(g, attn + roff * D, D, h->wp<void>(b + "attn.proj.weight"), 0, s));
+        }
+        WVN_PROPAGATE(layernorm_rows(x + roff * D, h->wp<float>(b + "norm2.weight"), h->wp<float>(b + "norm2.bias"),
+                                     xn + roff * D, nullptr, ls, s));
+        {
+          GemmArgs g;
+          g.M = srows; g.N = c.mlp_dim; g.K = D; g.epi = EPI_BF16; g.act = ACT_GELU;
+          g.bias = h->wp<float>(b + "mlp.fc1.bias"); g.out = h->hid.p; g.ldo = c.mlp_dim;  // hid is reused per sub-chunk
+          WVN_PROPAGATE(gemm_bf16(g, xn + roff * D, D, h->wp<void>(b + "mlp.fc1.weight"), 0, s));
+        }
+        {
+          GemmArgs g;
+          g.M = srows; g.N = D; g.K = c.mlp_dim; g.epi = EPI_RESID_F32; g.bias = h->wp<float>(b + "mlp.fc2.bias");
+          g.out = x + roff * D; g.ldo = D;
+          WVN_PROPAGATE(gemm_bf16(g, h->hid.p, c.mlp_dim, h->wp<void>(b + "mlp.fc2.weight"), 0, s));
+        }
       }
     }
     __nv_bfloat16* tok_bf = reinterpret_cast<__nv_bfloat16*>(h->tok_bf16.p) + static_cast<long long>(b0) * h->npad * D;

@@ -31,8 +31,8 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiThreads = 256;
 constexpr int kMaxSmemBytes = 227 * 1024;
 constexpr int kDefaultCluster = 1;  // thread-block cluster size for weight-tile multicast (tuned on B200)
-constexpr int kEpiBufBytes = 4096;                            // one 32-row x 128-byte staging tile
-constexpr int kEpiStageBytes = 8 * 2 * kEpiBufBytes;          // 8 epilogue warps x 2 buffers (TMA-store staging)
+constexpr int kEpiBufBytes = 4096;                            // one 32-row x 128-byte transpose tile
+constexpr int kEpiStageBytes = 8 * kEpiBufBytes;              // one per epilogue warp
 constexpr int kFixedSmemBytes = 1024 /*barriers + scratch*/ + kEpiStageBytes + 1024 /*align slack*/;
 
 // Tile enumeration.  Default: tile ids run n-fastest over the whole (m, n) grid and are
@@ -105,7 +105,6 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int BN, int EPI, int ACT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                  const GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   constexpr int kMaxStages = 8;
@@ -140,7 +139,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int crank = cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
   float* row_acc = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);  // [128] EPI_MLP_HEAD scratch
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;         // [8 warps][2][4 KB] TMA-store staging
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;         // [8 warps][4 KB] epilogue transpose tiles
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -249,7 +248,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     float head_partial = 0.f;
-    uint32_t stg_cnt = 0;  // staging-buffer parity of this warp's TMA stores
     if (EPI == EPI_MLP_HEAD && half == 0) row_acc[row_in_tile] = 0.f;
     if (EPI == EPI_MLP_HEAD) asm volatile("bar.sync 1, 256;" ::: "memory");
     for (TileIter<ROW_OWNER> it(num_m, num_n, bres, cs, crank); it.valid(); it.next()) {
@@ -302,51 +300,74 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ACT);
         }
-        // ---- stores through the TMA: the 32x32 chunk of this warp is staged in shared memory in the
-        // swizzled layout the tensor map expects, then one lane issues a bulk tensor store (or, for the
-        // residual stream, a bulk reduce-add: x += acc + bias happens at L2, no residual load at all).
-        // Per-thread row-wise stores were LSU-wavefront-bound (every 16-byte piece of a lane lies in a
-        // different 128-byte line): measured 7.6k-19k clk/tile of epilogue against 2.3k clk of MMA.
-        constexpr bool kTmaEpi = (EPI == EPI_BF16 || EPI == EPI_F32 || EPI == EPI_RESID_F32 || EPI == EPI_QKV);
+        // ---- coalesced stores: the 32x32 chunk (lane = row) is transposed through a swizzled shared-
+        // memory tile so that each store instruction writes whole row segments (lanes along columns).
+        // Per-thread row-wise stores were LSU-wavefront-bound — every 16-byte piece of a lane lies in a
+        // different 128-byte line (measured 7.6k-19k clk/tile of epilogue against 2.3k clk of MMA) — and
+        // TMA stores queue behind the mainloop's in-flight TMA loads.  The residual stream is updated
+        // with vector reductions (red.global.add.v4.f32): x += acc + bias happens at L2, no load.
+        constexpr bool kStagedEpi = (EPI == EPI_BF16 || EPI == EPI_F32 || EPI == EPI_RESID_F32 || EPI == EPI_QKV);
         bool qkv_is_v = false;
         if (EPI == EPI_QKV) qkv_is_v = (col0 >= 2 * args.dim);
-        if (kTmaEpi && !qkv_is_v) {
-          uint8_t* buf = epi_stage + ((warp - kEpiWarp0) * 2 + (stg_cnt & 1)) * kEpiBufBytes;
-          if (lane == 0) tma_store_wait_read<1>();  // the store that last read this buffer has drained it
-          __syncwarp();
+        if (kStagedEpi && !qkv_is_v) {
+          uint8_t* buf = epi_stage + (warp - kEpiWarp0) * kEpiBufBytes;
+          const int row_base = m_blk * BM + quarter * 32;
+          __syncwarp();  // the previous chunk's read-back is complete
           if (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q)  // 128-byte rows, 128B swizzle: 16-byte chunk q of row r -> q ^ (r & 7)
+            for (int q = 0; q < 8; ++q)  // 128-byte rows: 16-byte chunk q of row r lives at q ^ (r & 7)
               *reinterpret_cast<float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
                   make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            __syncwarp();
+            float* outp = reinterpret_cast<float*>(args.out);
+            const int q = lane & 7;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {  // 4 rows x 128 B per instruction
+              const int r = it * 4 + (lane >> 3);
+              const float4 val = *reinterpret_cast<const float4*>(buf + r * 128 + ((q ^ (r & 7)) << 4));
+              if (row_base + r < args.M) {
+                float* dst = outp + static_cast<long long>(row_base + r) * args.ldo + col0 + q * 4;
+                if (EPI == EPI_RESID_F32) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y),
+                               "f"(val.z), "f"(val.w)
+                               : "memory");
+                } else {
+                  *reinterpret_cast<float4*>(dst) = val;
+                }
+              }
+            }
           } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)  // 64-byte rows, 64B swizzle: chunk q of row r -> q ^ ((r >> 1) & 3)
+            for (int q = 0; q < 4; ++q)  // 64-byte rows: chunk q of row r lives at q ^ ((r >> 1) & 3)
               *reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
                   make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            const int row_base = m_blk * BM + quarter * 32;
-            if (EPI == EPI_F32 || EPI == EPI_BF16) {
-              tma_store_2d(&tmap_c, buf, col0, row_base);
-            } else if (EPI == EPI_RESID_F32) {
-              tma_reduce_add_2d(&tmap_c, buf, col0, row_base);
-            } else {  // Q / K: [b*h, npad, 64] seen as a 2-D [b*h*npad, 64] tensor
+            __syncwarp();
+            __nv_bfloat16* base;
+            long long row_stride, first;
+            if (EPI == EPI_BF16) {
+              base = reinterpret_cast<__nv_bfloat16*>(args.out);
+              row_stride = args.ldo;
+              first = static_cast<long long>(row_base) * args.ldo + col0;
+            } else {  // Q / K: [b*h, npad, 64]
               const int which = col0 / args.dim;
               const int within = col0 - which * args.dim;
               const int fr = row_base / args.npad, tk0 = row_base - fr * args.npad;
-              const int orow = (fr * args.heads + (within >> 6)) * args.npad + tk0;
-              tma_store_2d(which == 0 ? &tmap_c : &tmap_c2, buf, within & 63, orow);
+              base = reinterpret_cast<__nv_bfloat16*>(which == 0 ? args.q : args.k);
+              row_stride = 64;
+              first = ((static_cast<long long>(fr) * args.heads + (within >> 6)) * args.npad + tk0) * 64 + (within & 63);
             }
-            tma_store_commit();
+            const int q = lane & 3;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {  // 8 rows x 64 B per instruction
+              const int r = it * 8 + (lane >> 2);
+              const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+              if (row_base + r < args.M) *reinterpret_cast<uint4*>(base + first + r * row_stride + q * 8) = val;
+            }
           }
-          ++stg_cnt;
         }
         if (!row_ok) {
-          // out-of-range tail row: no per-row work below (TMA stores clip rows >= M themselves)
+          // out-of-range tail row: no per-row work below
         } else if (EPI == EPI_PATCH) {
           const float4* p4 = reinterpret_cast<const float4*>(args.pos + static_cast<long long>(1 + tok) * args.ldo + col0);
           float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + out_row * args.ldo + col0);
@@ -415,7 +436,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
-    if (lane == 0) tma_store_wait_all<0>();  // all bulk stores of this warp have completed
   }
 
   tc_fence_before();
@@ -440,8 +460,7 @@ int bres_env_mode() {
 }
 
 template <int BN, int EPI, int ACT>
-int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                const CUtensorMap& tc2, cudaStream_t stream) {
+int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_bf16_kernel<BN, EPI, ACT>;
   static bool attr_set = false;
@@ -487,9 +506,9 @@ int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    WVN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tc2, launch_args));
+    WVN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, launch_args));
   } else {
-    kern<<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, tc, tc2, launch_args);
+    kern<<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, launch_args);
   }
   prof_end(PROF_GEMM, stream);
   WVN_CHECK_LAUNCH("gemm_bf16_kernel");
@@ -497,28 +516,27 @@ int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
 }
 
 template <int BN>
-int dispatch_epi(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                 const CUtensorMap& tc2, cudaStream_t s) {
+int dispatch_epi(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t s) {
   switch (a.epi) {
     case EPI_BF16:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_BF16, ACT_NONE>(a, ta, tb, tc, tc2, s);
-      if (a.act == ACT_RELU) return launch_gemm<BN, EPI_BF16, ACT_RELU>(a, ta, tb, tc, tc2, s);
-      if (a.act == ACT_GELU) return launch_gemm<BN, EPI_BF16, ACT_GELU>(a, ta, tb, tc, tc2, s);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_BF16, ACT_NONE>(a, ta, tb, s);
+      if (a.act == ACT_RELU) return launch_gemm<BN, EPI_BF16, ACT_RELU>(a, ta, tb, s);
+      if (a.act == ACT_GELU) return launch_gemm<BN, EPI_BF16, ACT_GELU>(a, ta, tb, s);
       break;
     case EPI_F32:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_F32, ACT_NONE>(a, ta, tb, tc, tc2, s);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_F32, ACT_NONE>(a, ta, tb, s);
       break;
     case EPI_RESID_F32:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_RESID_F32, ACT_NONE>(a, ta, tb, tc, tc2, s);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_RESID_F32, ACT_NONE>(a, ta, tb, s);
       break;
     case EPI_PATCH:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_PATCH, ACT_NONE>(a, ta, tb, tc, tc2, s);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_PATCH, ACT_NONE>(a, ta, tb, s);
       break;
     case EPI_QKV:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_QKV, ACT_NONE>(a, ta, tb, tc, tc2, s);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_QKV, ACT_NONE>(a, ta, tb, s);
       break;
     case EPI_MLP_HEAD:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_MLP_HEAD, ACT_NONE>(a, ta, tb, tc, tc2, s);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_MLP_HEAD, ACT_NONE>(a, ta, tb, s);
       break;
   }
   return set_error(WVN_ERR_INVALID, "gemm: unsupported epilogue/activation combination (%d, %d)", a.epi, a.act);
@@ -575,26 +593,14 @@ int gemm_bf16(const GemmArgs& a, const void* A, long long lda, const void* W, in
   CUtensorMap ta, tb;
   WVN_PROPAGATE(make_tmap_bf16_2d(&ta, A, a.K, a.M, static_cast<uint64_t>(lda) * 2, BK, BM));
   WVN_PROPAGATE(make_tmap_bf16_2d(&tb, W, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, block_n / b.cluster));
-  // output tensor maps for the TMA-store epilogues (32 x 32 boxes; fp32: 128B swizzle, bf16: 64B swizzle)
-  CUtensorMap tc = ta, tc2 = ta;
-  if (a.epi == EPI_F32 || a.epi == EPI_RESID_F32) {
-    WVN_REQUIRE(a.ldo % 4 == 0, "gemm: fp32 output pitch must be a multiple of 4");
-    WVN_PROPAGATE(make_tmap_2d(&tc, a.out, 4, a.N, a.M, static_cast<uint64_t>(a.ldo) * 4, 32, 32, 128));
-  } else if (a.epi == EPI_BF16) {
-    WVN_REQUIRE(a.ldo % 8 == 0, "gemm: bf16 output pitch must be a multiple of 8");
-    WVN_PROPAGATE(make_tmap_2d(&tc, a.out, 2, a.N, a.M, static_cast<uint64_t>(a.ldo) * 2, 32, 32, 64));
-  } else if (a.epi == EPI_QKV) {
-    const uint64_t rows = static_cast<uint64_t>(a.M / a.npad) * a.heads * a.npad;
-    WVN_REQUIRE(a.M % a.npad == 0, "gemm: QKV rows must be whole frames");
-    WVN_PROPAGATE(make_tmap_2d(&tc, a.q, 2, 64, rows, 128, 32, 32, 64));
-    WVN_PROPAGATE(make_tmap_2d(&tc2, a.k, 2, 64, rows, 128, 32, 32, 64));
-  }
+  if (a.epi == EPI_F32 || a.epi == EPI_RESID_F32) WVN_REQUIRE(a.ldo % 4 == 0, "gemm: fp32 output pitch must be a multiple of 4");
+  if (a.epi == EPI_BF16) WVN_REQUIRE(a.ldo % 8 == 0, "gemm: bf16 output pitch must be a multiple of 8");
   switch (block_n) {
-    case 64: return dispatch_epi<64>(b, ta, tb, tc, tc2, stream);
-    case 128: return dispatch_epi<128>(b, ta, tb, tc, tc2, stream);
-    case 192: return dispatch_epi<192>(b, ta, tb, tc, tc2, stream);
-    case 224: return dispatch_epi<224>(b, ta, tb, tc, tc2, stream);
-    case 256: return dispatch_epi<256>(b, ta, tb, tc, tc2, stream);
+    case 64: return dispatch_epi<64>(b, ta, tb, stream);
+    case 128: return dispatch_epi<128>(b, ta, tb, stream);
+    case 192: return dispatch_epi<192>(b, ta, tb, stream);
+    case 224: return dispatch_epi<224>(b, ta, tb, stream);
+    case 256: return dispatch_epi<256>(b, ta, tb, stream);
   }
   return set_error(WVN_ERR_INVALID, "gemm: unreachable");
 }
