@@ -94,23 +94,41 @@ pixel_head_kernel(const __grid_constant__ CUtensorMap tmap_w2, const PixelHeadAr
     const float* gub = a.gu + static_cast<long long>(b) * P * a.ldg;
 
     // ---------------- phase A: vertical blend of the token window (G | U | cT) + |x|^2 ingredients
-    for (int i = threadIdx.x; i < kTileH * a.ww * (kGvStride / 4); i += kThreads) {
-      const int v4 = i % (kGvStride / 4);
-      const int c = (i / (kGvStride / 4)) % a.ww;
-      const int r = i / ((kGvStride / 4) * a.ww);
-      int y0;
-      float wy;
-      ac_true(py0 + r, a.sy, a.gh, y0, wy);
-      const int y1 = min(y0 + 1, a.gh - 1);
-      const int tc = min(cx0 + c, a.gw - 1);
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gub + (static_cast<long long>(y0) * a.gw + tc) * a.ldg) + v4);
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gub + (static_cast<long long>(y1) * a.gw + tc) * a.ldg) + v4);
-      float4 o;
-      o.x = (1.f - wy) * g0.x + wy * g1.x;
-      o.y = (1.f - wy) * g0.y + wy * g1.y;
-      o.z = (1.f - wy) * g0.z + wy * g1.z;
-      o.w = (1.f - wy) * g0.w + wy * g1.w;
-      reinterpret_cast<float4*>(gv + (r * a.ww + c) * kGvStride)[v4] = o;
+    {
+      // all global loads of this thread are issued before any is consumed (one L2 latency per tile, not one
+      // per loop trip): at most kTileH * kWinMax * 73 / 256 = 6 float4 pairs per thread
+      constexpr int kMaxIt = (kTileH * kWinMax * (kGvStride / 4) + kThreads - 1) / kThreads;
+      const int n_items = kTileH * a.ww * (kGvStride / 4);
+      float4 g0[kMaxIt], g1[kMaxIt];
+      float wys[kMaxIt];
+#pragma unroll
+      for (int it = 0; it < kMaxIt; ++it) {
+        const int i = threadIdx.x + it * kThreads;
+        if (i < n_items) {
+          const int v4 = i % (kGvStride / 4);
+          const int c = (i / (kGvStride / 4)) % a.ww;
+          const int r = i / ((kGvStride / 4) * a.ww);
+          int y0;
+          ac_true(py0 + r, a.sy, a.gh, y0, wys[it]);
+          const int y1 = min(y0 + 1, a.gh - 1);
+          const int tc = min(cx0 + c, a.gw - 1);
+          g0[it] = __ldg(reinterpret_cast<const float4*>(gub + (static_cast<long long>(y0) * a.gw + tc) * a.ldg) + v4);
+          g1[it] = __ldg(reinterpret_cast<const float4*>(gub + (static_cast<long long>(y1) * a.gw + tc) * a.ldg) + v4);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < kMaxIt; ++it) {
+        const int i = threadIdx.x + it * kThreads;
+        if (i < n_items) {
+          const float wy = wys[it];
+          float4 o;
+          o.x = (1.f - wy) * g0[it].x + wy * g1[it].x;
+          o.y = (1.f - wy) * g0[it].y + wy * g1[it].y;
+          o.z = (1.f - wy) * g0[it].z + wy * g1[it].z;
+          o.w = (1.f - wy) * g0[it].w + wy * g1[it].w;
+          reinterpret_cast<float4*>(gv)[i] = o;  // i == (r * ww + c) * (kGvStride / 4) + v4
+        }
+      }
     }
     if (threadIdx.x < kTileH * a.ww) {
       // xv_c = (1-wy) t[y0,c] + wy t[y1,c]:  |xv_c|^2 and xv_c . xv_{c+1} from the per-token Gram entries
