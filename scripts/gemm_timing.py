@@ -11,6 +11,10 @@ for (N, K, kind, act, name) in [(1152, 384, 0, 0, "qkv-like bf16"), (1536, 384, 
         ops.gemm_bf16(a, w, bias, out_kind=kind, act=act, out=out)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); ops.gemm_bf16(a, w, bias, out_kind=kind, act=act, out=out); e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    reps = int(os.environ.get("REPS", "1"))
+    e0.record()
+    for _ in range(reps):
+        ops.gemm_bf16(a, w, bias, out_kind=kind, act=act, out=out)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
     print(f"{name}: {ms*1000:.1f} us  {2*M*N*K/ms/1e9:.0f} TFLOP/s", flush=True)

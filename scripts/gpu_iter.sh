@@ -1,7 +1,7 @@
-timeout 300 python -m pytest tests/test_path_gpu.py -q --tb=short -s -k "pixel" 2>&1 | grep -E "diff|passed|failed|Error" | tail -4
-timeout 300 python bench.py --steps 5 --warmup 2 --cpu-frames 0 2>gpurun_out/bench_iter.err | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('fps',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'attn TF',round(d['roofline']['achieved'],1),'attn share',round(d['roofline']['share_of_step'],3),'gemm share',round(d['roofline']['gemm_share_of_step'],3))"
-tail -3 gpurun_out/bench_iter.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:pixel_head_kernel -s 1 -c 1 -o gpurun_out/pixel_head -f \
-   python bench.py --profile-only --steps 1 --warmup 1 --batch 8 > gpurun_out/ncu_ph.log 2>&1
+#!/bin/bash
+# iteration script (rewritten per experiment)
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+WVN_GEMM_PAIR=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_kernel --launch-skip 5 --launch-count 1 -f -o gpurun_out/gemm_fc1 python scripts/gemm_timing.py 2>&1 | tail -5
+WVN_GEMM_PAIR=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_kernel --launch-skip 11 --launch-count 1 -f -o gpurun_out/gemm_proj python scripts/gemm_timing.py 2>&1 | tail -3
+ls -la gpurun_out/*.ncu-rep

@@ -26,6 +26,8 @@ def ops():
 @pytest.mark.parametrize("M,N,K,bn", [
     (128, 128, 64, 128), (300, 384, 384, 0), (1000, 1152, 384, 192), (777, 1536, 384, 256), (512, 384, 1536, 0),
     (130, 448, 64, 224), (4096, 64, 256, 64), (128 * 150, 384, 192, 128), (25600, 1152, 384, 0), (12800, 1536, 384, 0),
+    # CTA-pair kernel: odd 128-row block count + row tail, streaming (K=1536), 256- and 128-wide resident tiles
+    (25600 + 128 + 37, 1152, 384, 0), (20000, 384, 1536, 0), (19200, 512, 384, 0), (19000, 640, 128, 128),
 ])
 @pytest.mark.parametrize("out_kind,act", [(0, 0), (0, 1), (0, 2), (1, 0), (2, 0)])
 def test_gemm(ops, M, N, K, bn, out_kind, act):

@@ -134,17 +134,24 @@ int wvn_gemm_bf16(const void* a, long long lda, const void* w, const float* bias
   g.epi = out_kind == 0 ? EPI_BF16 : (out_kind == 1 ? EPI_F32 : EPI_RESID_F32);
   WVN_REQUIRE(out_kind >= 0 && out_kind <= 2, "wvn_gemm_bf16: out_kind %d", out_kind);
   g.act = act; g.bias = bias; g.out = out; g.ldo = ldo;
+  {
+    static int dbg = -1;  // $WVN_GEMM_DEBUG: kernel experiments only (1 = no stores, 2 = no epilogue); never set in production
+    if (dbg < 0) { const char* e = getenv("WVN_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    g.debug = dbg;
+  }
 #ifdef WVN_GEMM_TIMING
-  static long long* tbuf = nullptr;
-  if (!tbuf) cudaMallocManaged(&tbuf, 8 * sizeof(long long));
-  for (int i = 0; i < 8; ++i) tbuf[i] = 0;
+  static long long* tbuf = nullptr;  // device memory: the probes must not fault on managed pages
+  if (!tbuf) cudaMalloc(&tbuf, 8 * sizeof(long long));
+  cudaMemsetAsync(tbuf, 0, 8 * sizeof(long long), S(stream));
   g.timing = tbuf;
   const int rc = gemm_bf16(g, a, lda, w, block_n, S(stream));
+  long long t[8];
+  cudaMemcpyAsync(t, tbuf, sizeof(t), cudaMemcpyDeviceToHost, S(stream));
   cudaStreamSynchronize(S(stream));
-  const long long nt = tbuf[3] > 0 ? tbuf[3] : 1;
+  const long long nt = t[3] > 0 ? t[3] : 1;
   fprintf(stderr, "[gemm timing M=%d N=%d K=%d kind=%d act=%d, cycles per tile of CTA 0 (%lld tiles)] mma: wait_acc_empty %lld  "
           "wait_full(TMA) %lld  issue+commit %lld | epilogue: wait_acc_full %lld  work %lld\n",
-          m, n, k, out_kind, act, nt, tbuf[0] / nt, tbuf[1] / nt, tbuf[2] / nt, tbuf[4] / nt, tbuf[5] / nt);
+          m, n, k, out_kind, act, nt, t[0] / nt, t[1] / nt, t[2] / nt, t[4] / nt, t[5] / nt);
   return rc;
 #else
   return gemm_bf16(g, a, lda, w, block_n, S(stream));

@@ -7,7 +7,20 @@
 // the per-pixel traversability MLP K11): patch-embed, QKV, attention out-proj, MLP fc1/fc2,
 // the STEGO head and the 384->256->32 layers of the traversability MLP.
 //
-// Structure (one CTA per SM, persistent over output tiles, 384 threads):
+// Two kernels share the epilogue:
+//
+// gemm_pair_kernel (the ViT-sized problems) — a CTA PAIR (2-cluster, the two SMs of a TPC) computes a
+//   256 x BN tile with one tcgen05.mma.cta_group::2 stream issued by the leader CTA.  Each CTA stages only
+//   its own 128 rows of A and its own BN/2 rows of W, so per SM the L2 -> smem operand traffic per flop is
+//   (128 + BN/2) / (128 * BN) instead of (128 + BN) / (128 * BN); when K is small (384) each CTA's half of
+//   the [BN, K] weight slab stays RESIDENT in shared memory and the pair walks a contiguous run of m-tiles,
+//   so only activations stream.  These skinny-K GEMMs are bound by the chip-wide L2 -> SM throughput
+//   (~6.3 KB/clk ~= 42 B/clk/SM, measured), not by the tensor pipe: a 128 x 256 single-CTA tile needs
+//   96 B/clk/SM at full MMA rate, the resident pair needs 31.
+//
+// gemm_bf16_kernel (small problems, patch-embed, the row-owner MLP head) — one CTA per SM, 128 x BN tiles.
+//
+// Both: 384 threads, persistent over output tiles,
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
 //   warp 1      : MMA issuer     (single thread issues tcgen05.mma, commits to mbarriers)
 //   warp 2      : TMEM allocator (2 accumulator stages so epilogue(i) overlaps mainloop(i+1))
@@ -30,43 +43,46 @@ constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiThreads = 256;
 constexpr int kMaxSmemBytes = 227 * 1024;
-constexpr int kDefaultCluster = 1;  // thread-block cluster size for weight-tile multicast (tuned on B200)
 constexpr int kEpiBufBytes = 4096;                            // one 32-row x 128-byte transpose tile
 constexpr int kEpiStageBytes = 8 * kEpiBufBytes;              // one per epilogue warp
 constexpr int kFixedSmemBytes = 1024 /*barriers + scratch*/ + kEpiStageBytes + 1024 /*align slack*/;
+constexpr int kMaxStages = 8;
 
-// Tile enumeration.  Default: tile ids run n-fastest over the whole (m, n) grid and are
-// dealt round-robin to CTAs (neighbouring CTAs share the A tile through L2).  ROW_OWNER
-// (used by EPI_MLP_HEAD): a CTA owns whole 128-row blocks and visits their n-chunks in
-// order, so per-row reductions across n-chunks stay inside one CTA.
-// B_RESIDENT (runtime, K small): a CTA is pinned to one n-block whose whole [BN, K] weight slab
-// stays in shared memory; it walks the m-blocks slot, slot + S, ... (S = gridDim.x / num_n), so only
-// the activation tiles stream through L2 -> smem (the L2 -> SM path, ~42 B/clk/SM, is what bounds
-// these skinny-K GEMMs, not the tensor pipe).
+// Tile enumeration of the single-CTA kernel.  Default: tile ids run n-fastest over the whole (m, n)
+// grid and are dealt round-robin to CTAs (neighbouring CTAs share the A tile through L2).  ROW_OWNER
+// (used by EPI_MLP_HEAD): a CTA owns whole 128-row blocks and visits their n-chunks in order, so
+// per-row reductions across n-chunks stay inside one CTA.
 template <bool ROW_OWNER>
 struct TileIter {
-  int num_m, num_n, m_blk, n_blk, lin, step;
-  bool bres;
-  int cs, rank, m_grp, num_grp;  // cluster mode: the cs CTAs of a cluster walk (m-group, n) items in lockstep
-  __device__ TileIter(int nm, int nn, bool b_resident, int cluster = 1, int cta_rank = 0)
-      : num_m(nm), num_n(nn), m_blk(0), n_blk(0), lin(0), step(0), bres(b_resident), cs(cluster), rank(cta_rank),
-        m_grp(0), num_grp(0) {
-    if (cs > 1) {
-      num_grp = (num_m + cs - 1) / cs;
-      lin = blockIdx.x / cs; step = gridDim.x / cs;
-      m_grp = lin / num_n; n_blk = lin % num_n; m_blk = m_grp * cs + rank;
-    }
-    else if (bres) { n_blk = blockIdx.x % num_n; m_blk = blockIdx.x / num_n; step = gridDim.x / num_n; }
-    else if (ROW_OWNER) { m_blk = blockIdx.x; n_blk = 0; }
+  int num_m, num_n, m_blk, n_blk, lin;
+  __device__ TileIter(int nm, int nn) : num_m(nm), num_n(nn), m_blk(0), n_blk(0), lin(0) {
+    if (ROW_OWNER) { m_blk = blockIdx.x; n_blk = 0; }
     else { lin = blockIdx.x; m_blk = lin / num_n; n_blk = lin % num_n; }
   }
-  __device__ bool valid() const { return cs > 1 ? m_grp < num_grp : m_blk < num_m; }
+  __device__ bool valid() const { return m_blk < num_m; }
   __device__ void next() {
-    if (cs > 1) { lin += step; m_grp = lin / num_n; n_blk = lin % num_n; m_blk = m_grp * cs + rank; }
-    else if (bres) { m_blk += step; }
-    else if (ROW_OWNER) { if (++n_blk == num_n) { n_blk = 0; m_blk += gridDim.x; } }
+    if (ROW_OWNER) { if (++n_blk == num_n) { n_blk = 0; m_blk += gridDim.x; } }
     else { lin += gridDim.x; m_blk = lin / num_n; n_blk = lin % num_n; }
   }
+};
+
+// Work enumeration of the pair kernel: items are (n-block, pair-m-block) with a pair-m-block = 256 rows.
+// Resident weights: the grid is S x num_n pairs; pair p is pinned to n-block p % num_n (its slab is loaded
+// once) and walks the m-blocks slot, slot + S, ... with slot = p / num_n — the num_n pairs of a slot consume
+// the same activation rows at the same time, so those are fetched from HBM once and hit in L2 afterwards.
+// Streaming (large K): items run n-fastest and are dealt round-robin, with the same L2 sharing of A.
+struct PairIter {
+  int lin, end, stride, num_n, n_fixed;
+  bool resident;
+  __device__ PairIter(int num_mp, int nn, bool res) : num_n(nn), n_fixed(0), resident(res) {
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    if (resident) { n_fixed = pair % nn; lin = pair / nn; stride = npairs / nn; end = num_mp; }
+    else { lin = pair; stride = npairs; end = num_mp * nn; }
+  }
+  __device__ bool valid() const { return lin < end; }
+  __device__ void next() { lin += stride; }
+  __device__ int mp() const { return resident ? lin : lin / num_n; }
+  __device__ int n() const { return resident ? n_fixed : lin % num_n; }
 };
 
 template <int BN>
@@ -75,55 +91,237 @@ struct GemmCfg {
   static constexpr uint32_t kBBytes = BN * BK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = (kMaxSmemBytes - kFixedSmemBytes) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
   static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kFixedSmemBytes;
+  static constexpr uint32_t kBHalfBytes = (BN / 2) * BK * 2;  // pair kernel: this CTA's half of a weight k-block
 };
 
-// GELU(x) = x * Phi(x) with the erf form's Phi, evaluated as Phi(-|x|) = 2^p(|x|) (degree-5 minimax fit of
-// log2 Phi(-t) on [0, 5.5], clamped beyond): max |error| 1.5e-6 in GELU — three orders below the bf16
-// rounding of the output — at 1 MUFU + ~9 FMA/ALU ops instead of erff's ~30 (the fc1 epilogue was
-// issue-bound on erff).
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float t = fminf(fabsf(x), 5.5f);
-  float p = fmaf(-0.0003865310864f, t, 0.006509808358f);
-  p = fmaf(p, t, -0.05048002675f);
-  p = fmaf(p, t, -0.4613505006f);
-  p = fmaf(p, t, -1.150225043f);
-  p = fmaf(p, t, -1.00010848f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p));
-  return x * (x >= 0.f ? 1.f - e : e);
+// GELU(x) = x * Phi(x) with the erf form's Phi.  Phi(-|x|) = 2^p(|x|) (degree-5 minimax fit of log2 Phi(-t) on
+// [0, 5.5], clamped beyond) and GELU(x) = max(x, 0) - t * Phi(-t), t = min(|x|, 5.5): max |error| 1.5e-6 —
+// three orders below the bf16 rounding of the output.  Two elements per call so that the polynomial runs on
+// packed FFMA2: 1 MUFU + ~5.5 FMA/ALU issue slots per element instead of erff's ~30 (the fc1 epilogue is
+// issue-bound).
+__device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
+  const float t0 = fminf(fabsf(x0), 5.5f), t1 = fminf(fabsf(x1), 5.5f);
+  const uint64_t t = pack2(t0, t1);
+  uint64_t p = fma2(pack2(-0.0003865310864f, -0.0003865310864f), t, pack2(0.006509808358f, 0.006509808358f));
+  p = fma2(p, t, pack2(-0.05048002675f, -0.05048002675f));
+  p = fma2(p, t, pack2(-0.4613505006f, -0.4613505006f));
+  p = fma2(p, t, pack2(-1.150225043f, -1.150225043f));
+  p = fma2(p, t, pack2(-1.00010848f, -1.00010848f));
+  float p0, p1, e0, e1;
+  unpack2(p, p0, p1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(p0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(p1));
+  x0 = fmaf(-t0, e0, fmaxf(x0, 0.f));
+  x1 = fmaf(-t1, e1, fmaxf(x1, 0.f));
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_GELU) return gelu_erf_fast(v);
-  return v;
-}
+#define WVN_DBG_STORE && args.debug != 1  // experiment knob ($WVN_GEMM_DEBUG through wvn_gemm_bf16): 1 = no global stores
 
+// One 128 x BN accumulator tile: TMEM -> registers -> bias / activation -> global memory.  Called by the 8 epilogue
+// warps (ewarp 0..7; ewarp & 3 must equal the hardware warp's TMEM lane quarter); m_blk / n_blk locate the tile in C.
+template <int BN, int EPI, int ACT>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32_t tmem_acc, const int m_blk, const int n_blk,
+                                              const int ewarp, const int lane, uint8_t* epi_stage, float& head_partial) {
+  const int quarter = ewarp & 3;  // TMEM lane quarter this warp may access
+  const int half = ewarp >> 2;    // which interleaved half of the 32-col chunks
+  const int row_in_tile = quarter * 32 + lane;
+  const int row = m_blk * BM + row_in_tile;
+  const bool row_ok = row < args.M;
+  constexpr int kChunksPerThread = (BN + 63) / 64;
+
+  // Per-row destination bookkeeping
+  long long out_row = row;
+  int tok = 0, frame = 0;
+  if (EPI == EPI_PATCH) {
+    frame = row / args.tokens_in;
+    tok = row - frame * args.tokens_in;
+    out_row = static_cast<long long>(frame) * args.npad + 1 + tok;
+  } else if (EPI == EPI_QKV) {
+    frame = row / args.npad;
+    tok = row - frame * args.npad;
+  }
+
+  if (args.debug == 2) return;  // experiment knob: accumulators are dropped
+  // The TMEM read of chunk i+1 is in flight while chunk i is converted and stored (two register buffers).
+  uint32_t rbuf[2][32];
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32;
+  tmem_ld32(taddr, rbuf[0]);
+#pragma unroll
+  for (int chunk_i = 0; chunk_i < kChunksPerThread; ++chunk_i) {  // the two column-halves interleave 32-col chunks
+    const int c0 = half * 32 + 64 * chunk_i;
+    if (c0 >= BN) break;
+    const int col0 = n_blk * BN + c0;
+    float4 bv[8];
+    if (args.bias != nullptr) {  // issued ahead of the TMEM wait
+      const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bv[j] = __ldg(b4 + j);
+    }
+    tmem_ld_wait();
+    if (chunk_i + 1 < kChunksPerThread && c0 + 64 < BN) tmem_ld32(taddr + 64 * (chunk_i + 1), rbuf[(chunk_i + 1) & 1]);
+    uint32_t(&r)[32] = rbuf[chunk_i & 1];
+    tmem_ld_fence32(r);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (args.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[4 * j + 0] += bv[j].x; v[4 * j + 1] += bv[j].y; v[4 * j + 2] += bv[j].z; v[4 * j + 3] += bv[j].w;
+      }
+    }
+    if (ACT == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (ACT == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
+    }
+    // ---- coalesced stores: the 32x32 chunk (lane = row) is transposed through a swizzled shared-
+    // memory tile so that each store instruction writes whole row segments (lanes along columns).
+    // Per-thread row-wise stores were LSU-wavefront-bound — every 16-byte piece of a lane lies in a
+    // different 128-byte line (measured 7.6k-19k clk/tile of epilogue against 2.3k clk of MMA) — and
+    // TMA stores queue behind the mainloop's in-flight TMA loads.  The residual stream is updated
+    // with vector reductions (red.global.add.v4.f32): x += acc + bias happens at L2, no load.
+    constexpr bool kStagedEpi = (EPI == EPI_BF16 || EPI == EPI_F32 || EPI == EPI_RESID_F32 || EPI == EPI_QKV);
+    bool qkv_is_v = false;
+    if (EPI == EPI_QKV) qkv_is_v = (col0 >= 2 * args.dim);
+    if (kStagedEpi && !qkv_is_v) {
+      uint8_t* buf = epi_stage + ewarp * kEpiBufBytes;
+      const int row_base = m_blk * BM + quarter * 32;
+      __syncwarp();  // the previous chunk's read-back is complete
+      if (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)  // 128-byte rows: 16-byte chunk q of row r lives at q ^ (r & 7)
+          *reinterpret_cast<float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        float* outp = reinterpret_cast<float*>(args.out);
+        const int q = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {  // 4 rows x 128 B per instruction
+          const int r = it * 4 + (lane >> 3);
+          const float4 val = *reinterpret_cast<const float4*>(buf + r * 128 + ((q ^ (r & 7)) << 4));
+          if (row_base + r < args.M WVN_DBG_STORE) {
+            float* dst = outp + static_cast<long long>(row_base + r) * args.ldo + col0 + q * 4;
+            if (EPI == EPI_RESID_F32) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y),
+                           "f"(val.z), "f"(val.w)
+                           : "memory");
+            } else {
+              *reinterpret_cast<float4*>(dst) = val;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)  // 64-byte rows: chunk q of row r lives at q ^ ((r >> 1) & 3)
+          *reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+              make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                         pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+        __syncwarp();
+        __nv_bfloat16* base;
+        long long row_stride, first;
+        if (EPI == EPI_BF16) {
+          base = reinterpret_cast<__nv_bfloat16*>(args.out);
+          row_stride = args.ldo;
+          first = static_cast<long long>(row_base) * args.ldo + col0;
+        } else {  // Q / K: [b*h, npad, 64]
+          const int which = col0 / args.dim;
+          const int within = col0 - which * args.dim;
+          const int fr = row_base / args.npad, tk0 = row_base - fr * args.npad;
+          base = reinterpret_cast<__nv_bfloat16*>(which == 0 ? args.q : args.k);
+          row_stride = 64;
+          first = ((static_cast<long long>(fr) * args.heads + (within >> 6)) * args.npad + tk0) * 64 + (within & 63);
+        }
+        const int q = lane & 3;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {  // 8 rows x 64 B per instruction
+          const int r = it * 8 + (lane >> 2);
+          const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+          if (row_base + r < args.M WVN_DBG_STORE) *reinterpret_cast<uint4*>(base + first + r * row_stride + q * 8) = val;
+        }
+      }
+    }
+    if (!row_ok) {
+      // out-of-range tail row: no per-row work below
+    } else if (EPI == EPI_PATCH) {
+      const float4* p4 = reinterpret_cast<const float4*>(args.pos + static_cast<long long>(1 + tok) * args.ldo + col0);
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + out_row * args.ldo + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 p = __ldg(p4 + j);
+        dst[j] = make_float4(v[4 * j] + p.x, v[4 * j + 1] + p.y, v[4 * j + 2] + p.z, v[4 * j + 3] + p.w);
+      }
+    } else if (EPI == EPI_MLP_HEAD) {
+      // columns [0, feat) = reconstruction of x, column trav_col = traversability logit
+      if (col0 < args.feat) {
+        const uint4* x4 = reinterpret_cast<const uint4*>(
+            reinterpret_cast<const __nv_bfloat16*>(args.x) + static_cast<long long>(row) * args.ldx + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 xv = __ldg(x4 + j);
+          const uint32_t w[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int c = col0 + 8 * j + 2 * t;
+            const float d0 = v[8 * j + 2 * t] - bf16_lo(w[t]);
+            const float d1 = v[8 * j + 2 * t + 1] - bf16_hi(w[t]);
+            if (c < args.feat) head_partial = fmaf(d0, d0, head_partial);
+            if (c + 1 < args.feat) head_partial = fmaf(d1, d1, head_partial);
+          }
+        }
+      } else if (col0 == args.trav_col) {
+        args.trav[row] = 1.f / (1.f + __expf(-v[0]));
+      }
+    } else if (EPI == EPI_QKV && qkv_is_v) {
+      // V is stored transposed ([b, h, d, token]) so that P·V consumes it K-major: lanes already run
+      // along tokens, so these direct stores are 64-byte coalesced per instruction.
+      const int within = col0 - 2 * args.dim;
+      const long long bh = static_cast<long long>(frame) * args.heads + (within >> 6);
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.vt) + (bh * 64 + (within & 63)) * args.npad + tok;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * args.npad] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+#ifdef WVN_GEMM_TIMING
+#define WVN_TM_DECL const bool timing = args.timing != nullptr && blockIdx.x == 0; long long tm[4] = {0, 0, 0, 0}, tprev = clock64(), ntiles = 0;
+#define WVN_TM(i) if (timing) { const long long tn = clock64(); tm[i] += tn - tprev; tprev = tn; }
+#define WVN_TM_TILE ++ntiles;
+#define WVN_TM_FLUSH if (timing) { for (int i = 0; i < 3; ++i) args.timing[i] = tm[i]; args.timing[3] = ntiles; }
+#else
+#define WVN_TM_DECL
+#define WVN_TM(i)
+#define WVN_TM_TILE
+#define WVN_TM_FLUSH
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// Single-CTA kernel: 128 x BN tiles, operands streamed through a kStages-deep TMA ring.
+// ------------------------------------------------------------------------------------------------
 template <int BN, int EPI, int ACT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmArgs args) {
   using Cfg = GemmCfg<BN>;
-  constexpr int kMaxStages = 8;
-  const bool bres = args.b_resident != 0;
-  // streaming mode: STAGES x (A, B) slots; B-resident mode: the [BN, K] slab + an A-only ring
-  const int STAGES = bres ? args.a_stages : Cfg::kStages;
+  constexpr int STAGES = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t b_region = bres ? static_cast<uint32_t>(args.K / BK) * Cfg::kBBytes : static_cast<uint32_t>(STAGES) * Cfg::kBBytes;
   uint8_t* smem_b = smem;
-  uint8_t* smem_a = smem + b_region;
+  uint8_t* smem_a = smem + STAGES * Cfg::kBBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + STAGES * Cfg::kABytes);
   uint64_t* full_bar = bars;                       // [kMaxStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * kMaxStages;      // [2]           MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * kMaxStages + 2; // [2]           epilogue -> MMA
-  uint64_t* b_full = bars + 2 * kMaxStages + 4;    // [1]           resident weight slab landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+  float* row_acc = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);  // [128] EPI_MLP_HEAD scratch
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;         // [8 warps][4 KB] epilogue transpose tiles
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,14 +330,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int num_n = args.N / BN;
   const int num_k = args.K / BK;
   constexpr bool ROW_OWNER = (EPI == EPI_MLP_HEAD);
-  // cluster mode (cs = 2 or 4 CTAs along M, same n-block): each CTA fetches 1/cs of every weight
-  // k-block and multicasts it to the whole cluster, cutting the L2 -> SM operand traffic that
-  // bounds these GEMMs (A: 16 KB + B: BN*128/cs bytes per CTA per k-block).
-  const int cs = args.cluster > 1 ? args.cluster : 1;
-  const int crank = cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-  const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
-  float* row_acc = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);  // [128] EPI_MLP_HEAD scratch
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;         // [8 warps][4 KB] epilogue transpose tiles
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -148,19 +338,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], cs);  // every CTA of the cluster must have drained the slot
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], kNumEpiThreads);
     }
-    mbar_init(b_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
-  if (cs > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts / arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -169,25 +357,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      if (bres) {
-        const int n_blk = blockIdx.x % num_n;
-        mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(num_k) * Cfg::kBBytes);
-        for (int kb = 0; kb < num_k; ++kb)
-          tma_load_2d(&tmap_b, b_full, smem_b + kb * Cfg::kBBytes, kb * BK, n_blk * BN);
-      }
-      for (TileIter<ROW_OWNER> it(num_m, num_n, bres, cs, crank); it.valid(); it.next()) {
-        const int m_blk = it.m_blk, n_blk = it.n_blk;
+      for (TileIter<ROW_OWNER> it(num_m, num_n); it.valid(); it.next()) {
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], bres ? Cfg::kABytes : Cfg::kStageBytes);
-          tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * BK, m_blk * BM);
-          if (cs > 1) {
-            const int rows = BN / cs;  // this CTA's slice of the weight tile, multicast to the cluster
-            tma_load_2d_mcast(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes + crank * rows * 128, kb * BK,
-                              n_blk * BN + crank * rows, cmask);
-          } else if (!bres) {
-            tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * BK, n_blk * BN);
-          }
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * BK, it.m_blk * BM);
+          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * BK, it.n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -200,15 +375,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      if (bres) mbar_wait(b_full, 0);
-#ifdef WVN_GEMM_TIMING
-      const bool timing = args.timing != nullptr && blockIdx.x == 0;
-      long long tm[4] = {0, 0, 0, 0}, tprev = clock64(), ntiles = 0;
-#define WVN_TM(i) if (timing) { const long long tn = clock64(); tm[i] += tn - tprev; tprev = tn; }
-#else
-#define WVN_TM(i)
-#endif
-      for (TileIter<ROW_OWNER> it(num_m, num_n, bres, cs, crank); it.valid(); it.next()) {
+      WVN_TM_DECL
+      for (TileIter<ROW_OWNER> it(num_m, num_n); it.valid(); it.next()) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         WVN_TM(0)
@@ -218,45 +386,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tc_fence_after();
           WVN_TM(1)
           const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + (bres ? kb : stage) * Cfg::kBBytes));
+          const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in (addr>>4) units
             umma_bf16_ss(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          // smem slot reusable once these MMAs retire (in cluster mode: tell every peer's producer)
-          if (cs > 1) umma_commit_mcast(&empty_bar[stage], cmask); else umma_commit(&empty_bar[stage]);
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           WVN_TM(2)
         }
         umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-#ifdef WVN_GEMM_TIMING
-        ++ntiles;
-#endif
+        WVN_TM_TILE
       }
-#ifdef WVN_GEMM_TIMING
-      if (timing) { for (int i = 0; i < 3; ++i) args.timing[i] = tm[i]; args.timing[3] = ntiles; }
-#endif
-#undef WVN_TM
+      WVN_TM_FLUSH
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------------ epilogue
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - kEpiWarp0) >> 2;     // which interleaved half of the 32-col chunks
-    const int row_in_tile = quarter * 32 + lane;
+    const int ewarp = warp - kEpiWarp0;
+    const int row_in_tile = (ewarp & 3) * 32 + lane;
+    const int half = ewarp >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     float head_partial = 0.f;
+#ifdef WVN_GEMM_TIMING
+    long long e_wait = 0, e_work = 0;
+#endif
     if (EPI == EPI_MLP_HEAD && half == 0) row_acc[row_in_tile] = 0.f;
     if (EPI == EPI_MLP_HEAD) asm volatile("bar.sync 1, 256;" ::: "memory");
-    for (TileIter<ROW_OWNER> it(num_m, num_n, bres, cs, crank); it.valid(); it.next()) {
-      const int m_blk = it.m_blk, n_blk = it.n_blk;
-      const int row = m_blk * BM + row_in_tile;
-      const bool row_ok = row < args.M;
-      constexpr int kChunksPerThread = (BN + 63) / 64;
+    for (TileIter<ROW_OWNER> it(num_m, num_n); it.valid(); it.next()) {
 #ifdef WVN_GEMM_TIMING
-      const bool etiming = args.timing != nullptr && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32;
       long long et0 = clock64();
 #endif
       mbar_wait(&acc_full[acc], acc_phase);
@@ -264,165 +424,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #ifdef WVN_GEMM_TIMING
       long long et1 = clock64();
 #endif
-
-      // Per-row destination bookkeeping
-      long long out_row = row;
-      int tok = 0, frame = 0;
-      if (EPI == EPI_PATCH) {
-        frame = row / args.tokens_in;
-        tok = row - frame * args.tokens_in;
-        out_row = static_cast<long long>(frame) * args.npad + 1 + tok;
-      } else if (EPI == EPI_QKV) {
-        frame = row / args.npad;
-        tok = row - frame * args.npad;
-      }
-
-#pragma unroll
-      for (int chunk_i = 0; chunk_i < kChunksPerThread; ++chunk_i) {  // the two column-halves interleave 32-col chunks
-        const int c0 = half * 32 + 64 * chunk_i;
-        if (c0 >= BN) break;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c0, r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + c0;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (args.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-          }
-        }
-        if (ACT != ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ACT);
-        }
-        // ---- coalesced stores: the 32x32 chunk (lane = row) is transposed through a swizzled shared-
-        // memory tile so that each store instruction writes whole row segments (lanes along columns).
-        // Per-thread row-wise stores were LSU-wavefront-bound — every 16-byte piece of a lane lies in a
-        // different 128-byte line (measured 7.6k-19k clk/tile of epilogue against 2.3k clk of MMA) — and
-        // TMA stores queue behind the mainloop's in-flight TMA loads.  The residual stream is updated
-        // with vector reductions (red.global.add.v4.f32): x += acc + bias happens at L2, no load.
-        constexpr bool kStagedEpi = (EPI == EPI_BF16 || EPI == EPI_F32 || EPI == EPI_RESID_F32 || EPI == EPI_QKV);
-        bool qkv_is_v = false;
-        if (EPI == EPI_QKV) qkv_is_v = (col0 >= 2 * args.dim);
-        if (kStagedEpi && !qkv_is_v) {
-          uint8_t* buf = epi_stage + (warp - kEpiWarp0) * kEpiBufBytes;
-          const int row_base = m_blk * BM + quarter * 32;
-          __syncwarp();  // the previous chunk's read-back is complete
-          if (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)  // 128-byte rows: 16-byte chunk q of row r lives at q ^ (r & 7)
-              *reinterpret_cast<float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            __syncwarp();
-            float* outp = reinterpret_cast<float*>(args.out);
-            const int q = lane & 7;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {  // 4 rows x 128 B per instruction
-              const int r = it * 4 + (lane >> 3);
-              const float4 val = *reinterpret_cast<const float4*>(buf + r * 128 + ((q ^ (r & 7)) << 4));
-              if (row_base + r < args.M) {
-                float* dst = outp + static_cast<long long>(row_base + r) * args.ldo + col0 + q * 4;
-                if (EPI == EPI_RESID_F32) {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y),
-                               "f"(val.z), "f"(val.w)
-                               : "memory");
-                } else {
-                  *reinterpret_cast<float4*>(dst) = val;
-                }
-              }
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)  // 64-byte rows: chunk q of row r lives at q ^ ((r >> 1) & 3)
-              *reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
-                  make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                             pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-            __syncwarp();
-            __nv_bfloat16* base;
-            long long row_stride, first;
-            if (EPI == EPI_BF16) {
-              base = reinterpret_cast<__nv_bfloat16*>(args.out);
-              row_stride = args.ldo;
-              first = static_cast<long long>(row_base) * args.ldo + col0;
-            } else {  // Q / K: [b*h, npad, 64]
-              const int which = col0 / args.dim;
-              const int within = col0 - which * args.dim;
-              const int fr = row_base / args.npad, tk0 = row_base - fr * args.npad;
-              base = reinterpret_cast<__nv_bfloat16*>(which == 0 ? args.q : args.k);
-              row_stride = 64;
-              first = ((static_cast<long long>(fr) * args.heads + (within >> 6)) * args.npad + tk0) * 64 + (within & 63);
-            }
-            const int q = lane & 3;
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {  // 8 rows x 64 B per instruction
-              const int r = it * 8 + (lane >> 2);
-              const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
-              if (row_base + r < args.M) *reinterpret_cast<uint4*>(base + first + r * row_stride + q * 8) = val;
-            }
-          }
-        }
-        if (!row_ok) {
-          // out-of-range tail row: no per-row work below
-        } else if (EPI == EPI_PATCH) {
-          const float4* p4 = reinterpret_cast<const float4*>(args.pos + static_cast<long long>(1 + tok) * args.ldo + col0);
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + out_row * args.ldo + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 p = __ldg(p4 + j);
-            dst[j] = make_float4(v[4 * j] + p.x, v[4 * j + 1] + p.y, v[4 * j + 2] + p.z, v[4 * j + 3] + p.w);
-          }
-        } else if (EPI == EPI_MLP_HEAD) {
-          // columns [0, feat) = reconstruction of x, column trav_col = traversability logit
-          if (col0 < args.feat) {
-            const uint4* x4 = reinterpret_cast<const uint4*>(
-                reinterpret_cast<const __nv_bfloat16*>(args.x) + static_cast<long long>(row) * args.ldx + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 xv = __ldg(x4 + j);
-              const uint32_t w[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int c = col0 + 8 * j + 2 * t;
-                const float d0 = v[8 * j + 2 * t] - bf16_lo(w[t]);
-                const float d1 = v[8 * j + 2 * t + 1] - bf16_hi(w[t]);
-                if (c < args.feat) head_partial = fmaf(d0, d0, head_partial);
-                if (c + 1 < args.feat) head_partial = fmaf(d1, d1, head_partial);
-              }
-            }
-          } else if (col0 == args.trav_col) {
-            args.trav[row] = 1.f / (1.f + __expf(-v[0]));
-          }
-        } else if (EPI == EPI_QKV && qkv_is_v) {
-          // V is stored transposed ([b, h, d, token]) so that P·V consumes it K-major: lanes already run
-          // along tokens, so these direct stores are 64-byte coalesced per instruction.
-          const int within = col0 - 2 * args.dim;
-          const long long bh = static_cast<long long>(frame) * args.heads + (within >> 6);
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.vt) + (bh * 64 + (within & 63)) * args.npad + tok;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * args.npad] = __float2bfloat16_rn(v[j]);
-        }
-      }
+      epilogue_tile<BN, EPI, ACT>(args, tmem_base + acc * BN, it.m_blk, it.n_blk, ewarp, lane, epi_stage, head_partial);
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 #ifdef WVN_GEMM_TIMING
-      if (etiming) { args.timing[4] += et1 - et0; args.timing[5] += clock64() - et1; }
+      e_wait += et1 - et0; e_work += clock64() - et1;
 #endif
 
-      if (EPI == EPI_MLP_HEAD && n_blk == num_n - 1) {
+      if (EPI == EPI_MLP_HEAD && it.n_blk == num_n - 1) {
         // combine the two column-halves of each row, then loss_reco -> confidence
+        const int row = it.m_blk * BM + row_in_tile;
         atomicAdd(&row_acc[row_in_tile], head_partial);
         head_partial = 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (half == 0) {
           const float loss = row_acc[row_in_tile] / static_cast<float>(args.feat);
           row_acc[row_in_tile] = 0.f;
-          if (row_ok) {
+          if (row < args.M) {
             // ConfidenceGenerator.inference_without_update (utils/confidence_generator.py:182-193)
             const float mean = __ldg(args.cg_mean), sd = __ldg(args.cg_std);
             const float shifted = mean + sd * args.cg_std_factor;
@@ -436,27 +455,185 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
+#ifdef WVN_GEMM_TIMING
+    if (args.timing != nullptr && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) { args.timing[4] = e_wait; args.timing[5] = e_work; }
+#endif
   }
 
   tc_fence_before();
   __syncthreads();
-  if (cs > 1) cluster_sync_all();  // no CTA may exit while peers can still write its smem / barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-// $WVN_GEMM_BRES: 0/unset = streaming tiles; 1 = weight-resident mode with 192-wide tiles where the
-// slab fits; 2 = weight-resident with 128-wide tiles (deeper activation ring).  Experiment knob.
-int bres_env_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("WVN_GEMM_BRES");
-    mode = e ? atoi(e) : 0;
-    if (mode < 0 || mode > 2) mode = 0;
+// ------------------------------------------------------------------------------------------------
+// CTA-pair kernel: 256 x BN tiles on tcgen05.mma.cta_group::2 (see the file header).
+//   shared memory per CTA:  [ W half-slab (resident: K/64 k-blocks | streaming: ring) ][ A ring ][ barriers ][ epilogue ]
+//   barriers: full[s]   leader only, 1 arrival (its expect_tx) + the bytes of BOTH CTAs' loads
+//             empty[s]  each CTA, signalled by the leader's multicast tcgen05.commit
+//             acc_full  each CTA (multicast commit);  acc_empty  leader only, 16 warp-arrivals (8 per CTA)
+//             b_full    leader only (resident slab landed);  b_empty  each CTA (slab may be overwritten)
+// ------------------------------------------------------------------------------------------------
+template <int BN, int EPI, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmArgs args) {
+  using Cfg = GemmCfg<BN>;
+  const bool resident = args.b_resident != 0;
+  const int STAGES = args.a_stages;
+  const int num_k = args.K / BK;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem;
+  uint8_t* smem_a = smem + static_cast<uint32_t>(resident ? num_k : STAGES) * Cfg::kBHalfBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + STAGES * Cfg::kABytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* acc_full = bars + 2 * kMaxStages;
+  uint64_t* acc_empty = bars + 2 * kMaxStages + 2;
+  uint64_t* b_full = bars + 2 * kMaxStages + 4;
+  uint64_t* b_empty = bars + 2 * kMaxStages + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int crank = static_cast<int>(cluster_ctarank());
+  const bool leader = crank == 0;
+
+  const int num_m = (args.M + BM - 1) / BM;
+  const int num_mp = (num_m + 1) / 2;
+  const int num_n = args.N / BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
   }
-  return mode;
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kMaxStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 16);
+    }
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / complete_tx
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0, cur_n = -1;
+      uint32_t phase = 0, be_phase = 0;
+      for (PairIter it(num_mp, num_n, resident); it.valid(); it.next()) {
+        const int mp = it.mp(), n = it.n();
+        const int b_row = n * BN + crank * (BN / 2);
+        if (resident && n != cur_n) {
+          if (cur_n >= 0) { mbar_wait(b_empty, be_phase); be_phase ^= 1; }  // every MMA on the old slab retired
+          if (leader) mbar_arrive_expect_tx(b_full, 2u * static_cast<uint32_t>(num_k) * Cfg::kBHalfBytes);
+          for (int kb = 0; kb < num_k; ++kb)
+            tma_load_2d_pair(&tmap_b, leader_smem_addr(b_full), smem_b + kb * Cfg::kBHalfBytes, kb * BK, b_row);
+          cur_n = n;
+        }
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t full_l = leader_smem_addr(&full_bar[stage]);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * (Cfg::kABytes + (resident ? 0u : Cfg::kBHalfBytes)));
+          tma_load_2d_pair(&tmap_a, full_l, smem_a + stage * Cfg::kABytes, kb * BK, (2 * mp + crank) * BM);
+          if (!resident) tma_load_2d_pair(&tmap_b, full_l, smem_b + stage * Cfg::kBHalfBytes, kb * BK, b_row);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      int stage = 0, acc = 0, cur_n = -1;
+      uint32_t phase = 0, acc_phase = 0, bf_phase = 0;
+      WVN_TM_DECL
+      for (PairIter it(num_mp, num_n, resident); it.valid(); it.next()) {
+        const int n = it.n();
+        if (resident && n != cur_n) { mbar_wait(b_full, bf_phase); bf_phase ^= 1; cur_n = n; }
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        WVN_TM(0)
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          WVN_TM(1)
+          const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + (resident ? kb : stage) * Cfg::kBHalfBytes));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_ss_pair(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage], 3);  // both CTAs' producers may refill the slot
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          WVN_TM(2)
+        }
+        umma_commit_pair(&acc_full[acc], 3);  // accumulator complete -> both CTAs' epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (resident) {
+          PairIter nx = it;
+          nx.next();
+          if (nx.valid() && nx.n() != n) umma_commit_pair(b_empty, 3);  // slab free once this tile's MMAs retire
+        }
+        WVN_TM_TILE
+      }
+      WVN_TM_FLUSH
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    const int ewarp = warp - kEpiWarp0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float unused = 0.f;
+#ifdef WVN_GEMM_TIMING
+    long long e_wait = 0, e_work = 0;
+#endif
+    for (PairIter it(num_mp, num_n, resident); it.valid(); it.next()) {
+#ifdef WVN_GEMM_TIMING
+      long long et0 = clock64();
+#endif
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+#ifdef WVN_GEMM_TIMING
+      long long et1 = clock64();
+#endif
+      epilogue_tile<BN, EPI, ACT>(args, tmem_base + acc * BN, 2 * it.mp() + crank, it.n(), ewarp, lane, epi_stage, unused);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(leader_smem_addr(&acc_empty[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#ifdef WVN_GEMM_TIMING
+      e_wait += et1 - et0; e_work += clock64() - et1;
+#endif
+    }
+#ifdef WVN_GEMM_TIMING
+    if (args.timing != nullptr && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) { args.timing[4] = e_wait; args.timing[5] = e_work; }
+#endif
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers / TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 template <int BN, int EPI, int ACT>
@@ -473,73 +650,107 @@ int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
   int grid = sm_count();
   if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
   if (grid > num_tiles) grid = num_tiles;
-  GemmArgs launch_args = a;
-  launch_args.b_resident = 0;
-  uint32_t smem_bytes = Cfg::kSmemBytes;
-  if (EPI != EPI_MLP_HEAD && (a.allow_b_resident || bres_env_mode() > 0)) {
-    const int slab = (a.K / BK) * static_cast<int>(Cfg::kBBytes);
-    const int a_stages = std::min<int>(8, (kMaxSmemBytes - kFixedSmemBytes - slab) / static_cast<int>(Cfg::kABytes));
-    const int per_n = grid / num_n;
-    if (a_stages >= 3 && per_n >= 1 && num_m >= 2 * per_n) {
-      launch_args.b_resident = 1;
-      launch_args.a_stages = a_stages;
-      grid = per_n * num_n;
-      smem_bytes = static_cast<uint32_t>(slab + a_stages * static_cast<int>(Cfg::kABytes) + kFixedSmemBytes);
-    }
-  }
   prof_begin(PROF_GEMM, stream);
-  if (a.cluster > 1) {
-    // thread-block cluster along M: grid must be a whole number of clusters
-    const int cs = a.cluster;
-    const int num_items = ((num_m + cs - 1) / cs) * num_n;
-    int clusters = sm_count() / cs;
-    if (clusters > num_items) clusters = num_items;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(clusters * cs);
-    cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    WVN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, launch_args));
-  } else {
-    kern<<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, launch_args);
-  }
+  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, a);
   prof_end(PROF_GEMM, stream);
   WVN_CHECK_LAUNCH("gemm_bf16_kernel");
   return WVN_OK;
 }
 
-template <int BN>
+// Pair-kernel geometry for a [N, K] weight: the half-slab stays resident when it leaves room for
+// at least 4 activation stages.
+struct PairPlan {
+  bool resident;
+  int a_stages;
+  uint32_t smem_bytes;
+};
+
+PairPlan plan_pair(int block_n, int K, bool allow_resident) {
+  const int half = (block_n / 2) * BK * 2;
+  const int slab = (K / BK) * half;
+  const int budget = kMaxSmemBytes - kFixedSmemBytes;
+  PairPlan p;
+  p.resident = allow_resident && slab + 4 * BM * BK * 2 <= budget;
+  p.a_stages = p.resident ? (budget - slab) / (BM * BK * 2) : budget / (BM * BK * 2 + half);
+  if (p.a_stages > kMaxStages) p.a_stages = kMaxStages;
+  p.smem_bytes = static_cast<uint32_t>(p.resident ? slab + p.a_stages * BM * BK * 2 : p.a_stages * (BM * BK * 2 + half)) +
+                 kFixedSmemBytes;
+  return p;
+}
+
+template <int BN, int EPI, int ACT>
+int launch_gemm_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+  auto kern = gemm_pair_kernel<BN, EPI, ACT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
+    attr_set = true;
+  }
+  const int num_m = (a.M + BM - 1) / BM, num_mp = (num_m + 1) / 2, num_n = a.N / BN;
+  const long long items = static_cast<long long>(num_mp) * num_n;
+  long long pairs = sm_count() / 2;
+  if (a.max_ctas > 0 && a.max_ctas / 2 < pairs) pairs = std::max(1, a.max_ctas / 2);
+  if (pairs > items) pairs = items;
+  PairPlan plan = plan_pair(BN, a.K, true);
+  if (plan.resident) {
+    if (pairs / num_n >= 1) pairs = (pairs / num_n) * num_n;  // S slots x num_n pinned n-blocks
+    else plan = plan_pair(BN, a.K, false);
+  }
+  GemmArgs la = a;
+  la.b_resident = plan.resident ? 1 : 0;
+  la.a_stages = plan.a_stages;
+  if (const char* e = getenv("WVN_GEMM_STAGES")) {  // experiment knob: cap the ring depth
+    const int cap = atoi(e);
+    if (cap >= 2 && cap < la.a_stages) la.a_stages = cap;
+  }
+  prof_begin(PROF_GEMM, stream);
+  kern<<<static_cast<unsigned>(2 * pairs), kNumThreads, plan.smem_bytes, stream>>>(ta, tb, la);
+  prof_end(PROF_GEMM, stream);
+  WVN_CHECK_LAUNCH("gemm_pair_kernel");
+  return WVN_OK;
+}
+
+template <int BN, bool PAIR>
 int dispatch_epi(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t s) {
+#define WVN_LAUNCH(E, A)                                            \
+  do {                                                              \
+    if (PAIR) return launch_gemm_pair<BN, E, A>(a, ta, tb, s);      \
+    return launch_gemm<BN, E, A>(a, ta, tb, s);                     \
+  } while (0)
   switch (a.epi) {
     case EPI_BF16:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_BF16, ACT_NONE>(a, ta, tb, s);
-      if (a.act == ACT_RELU) return launch_gemm<BN, EPI_BF16, ACT_RELU>(a, ta, tb, s);
-      if (a.act == ACT_GELU) return launch_gemm<BN, EPI_BF16, ACT_GELU>(a, ta, tb, s);
+      if (a.act == ACT_NONE) WVN_LAUNCH(EPI_BF16, ACT_NONE);
+      if (a.act == ACT_RELU) WVN_LAUNCH(EPI_BF16, ACT_RELU);
+      if (a.act == ACT_GELU) WVN_LAUNCH(EPI_BF16, ACT_GELU);
       break;
     case EPI_F32:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_F32, ACT_NONE>(a, ta, tb, s);
+      if (a.act == ACT_NONE) WVN_LAUNCH(EPI_F32, ACT_NONE);
       break;
     case EPI_RESID_F32:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_RESID_F32, ACT_NONE>(a, ta, tb, s);
-      break;
-    case EPI_PATCH:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_PATCH, ACT_NONE>(a, ta, tb, s);
+      if (a.act == ACT_NONE) WVN_LAUNCH(EPI_RESID_F32, ACT_NONE);
       break;
     case EPI_QKV:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_QKV, ACT_NONE>(a, ta, tb, s);
+      if (a.act == ACT_NONE) WVN_LAUNCH(EPI_QKV, ACT_NONE);
       break;
-    case EPI_MLP_HEAD:
-      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_MLP_HEAD, ACT_NONE>(a, ta, tb, s);
+    case EPI_PATCH:  // single-CTA kernel only (per-row scatter; one small GEMM per frame batch)
+      if (a.act == ACT_NONE && !PAIR) return launch_gemm<BN, EPI_PATCH, ACT_NONE>(a, ta, tb, s);
+      break;
+    case EPI_MLP_HEAD:  // single-CTA kernel only (row-owner tile order)
+      if (a.act == ACT_NONE && !PAIR) return launch_gemm<BN, EPI_MLP_HEAD, ACT_NONE>(a, ta, tb, s);
       break;
   }
+#undef WVN_LAUNCH
   return set_error(WVN_ERR_INVALID, "gemm: unsupported epilogue/activation combination (%d, %d)", a.epi, a.act);
+}
+
+// $WVN_GEMM_PAIR=0 forces the single-CTA kernel everywhere (A/B experiments, debugging).
+bool pair_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("WVN_GEMM_PAIR");
+    on = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+  }
+  return on != 0;
 }
 
 }  // namespace
@@ -556,15 +767,8 @@ int pick_block_n(int N) {
 int gemm_bf16(const GemmArgs& a, const void* A, long long lda, const void* W, int block_n, cudaStream_t stream) {
   WVN_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem (M=%d N=%d K=%d)", a.M, a.N, a.K);
   WVN_REQUIRE(a.K % BK == 0, "gemm: K=%d must be a multiple of %d (pad the operands)", a.K, BK);
-  if (block_n == 0) {
-    block_n = pick_block_n(a.N);
-    // prefer a 192-wide tile whose [192, K] weight slab can stay resident in shared memory
-    const int mode = a.allow_b_resident ? std::max(1, bres_env_mode()) : bres_env_mode();
-    if (mode == 1 && a.epi != EPI_MLP_HEAD && a.N % 192 == 0 && (a.K / BK) * 192 * 128 + 3 * 16384 + kFixedSmemBytes <= kMaxSmemBytes)
-      block_n = 192;
-    if (mode == 2 && a.epi != EPI_MLP_HEAD && a.N % 128 == 0 && (a.K / BK) * 128 * 128 + 3 * 16384 + kFixedSmemBytes <= kMaxSmemBytes)
-      block_n = 128;
-  }
+  const bool auto_n = block_n == 0;
+  if (auto_n) block_n = pick_block_n(a.N);
   WVN_REQUIRE(block_n == 64 || block_n == 128 || block_n == 192 || block_n == 224 || block_n == 256,
               "gemm: bad block_n %d", block_n);
   WVN_REQUIRE(a.N % block_n == 0, "gemm: N=%d must be a multiple of block_n=%d (pad the weights)", a.N, block_n);
@@ -576,31 +780,35 @@ int gemm_bf16(const GemmArgs& a, const void* A, long long lda, const void* W, in
   if (a.epi == EPI_QKV)
     WVN_REQUIRE(a.dim % 64 == 0 && a.N == 3 * a.dim && a.heads * 64 == a.dim && a.npad % 8 == 0,
                 "gemm: bad QKV epilogue geometry (dim=%d heads=%d npad=%d N=%d)", a.dim, a.heads, a.npad, a.N);
-  // Cluster multicast of the weight tile ($WVN_GEMM_CLUSTER = 1 | 2 | 4, default kDefaultCluster): only for
-  // streaming tiles with enough m-blocks to fill the machine, never with the row-owner head epilogue.
-  GemmArgs b = a;
-  static int env_cluster = -1;
-  if (env_cluster < 0) {
-    const char* e = getenv("WVN_GEMM_CLUSTER");
-    env_cluster = e ? atoi(e) : kDefaultCluster;
-    if (env_cluster != 1 && env_cluster != 2 && env_cluster != 4) env_cluster = kDefaultCluster;
-  }
-  const int num_m = (a.M + BM - 1) / BM;
-  b.cluster = 1;
-  if (a.epi != EPI_MLP_HEAD && !a.allow_b_resident && bres_env_mode() == 0 && env_cluster > 1 &&
-      num_m * (a.N / block_n) >= 2 * sm_count() && (block_n / env_cluster) % 8 == 0)
-    b.cluster = env_cluster;
-  CUtensorMap ta, tb;
-  WVN_PROPAGATE(make_tmap_bf16_2d(&ta, A, a.K, a.M, static_cast<uint64_t>(lda) * 2, BK, BM));
-  WVN_PROPAGATE(make_tmap_bf16_2d(&tb, W, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, block_n / b.cluster));
   if (a.epi == EPI_F32 || a.epi == EPI_RESID_F32) WVN_REQUIRE(a.ldo % 4 == 0, "gemm: fp32 output pitch must be a multiple of 4");
   if (a.epi == EPI_BF16) WVN_REQUIRE(a.ldo % 8 == 0, "gemm: bf16 output pitch must be a multiple of 8");
+
+  // CTA-pair kernel: whenever the problem has at least one 256-row item per pair of SMs and a pair-capable
+  // tile width (256 / 192 / 128, both halves a whole number of 8-row swizzle groups).
+  int pair_n = 0;
+  if (pair_enabled() && a.pair_mode >= 0 && a.epi != EPI_PATCH && a.epi != EPI_MLP_HEAD) {
+    if (!auto_n) pair_n = (block_n == 256 || block_n == 192 || block_n == 128) ? block_n : 0;
+    else pair_n = a.N % 256 == 0 ? 256 : a.N % 192 == 0 ? 192 : a.N % 128 == 0 ? 128 : 0;
+    const long long items = pair_n ? static_cast<long long>(((a.M + BM - 1) / BM + 1) / 2) * (a.N / pair_n) : 0;
+    if (items < sm_count() / 2 && a.pair_mode <= 0) pair_n = 0;
+  }
+  CUtensorMap ta, tb;
+  WVN_PROPAGATE(make_tmap_bf16_2d(&ta, A, a.K, a.M, static_cast<uint64_t>(lda) * 2, BK, BM));
+  if (pair_n) {
+    WVN_PROPAGATE(make_tmap_bf16_2d(&tb, W, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, pair_n / 2));
+    switch (pair_n) {
+      case 128: return dispatch_epi<128, true>(a, ta, tb, stream);
+      case 192: return dispatch_epi<192, true>(a, ta, tb, stream);
+      case 256: return dispatch_epi<256, true>(a, ta, tb, stream);
+    }
+  }
+  WVN_PROPAGATE(make_tmap_bf16_2d(&tb, W, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, block_n));
   switch (block_n) {
-    case 64: return dispatch_epi<64>(b, ta, tb, stream);
-    case 128: return dispatch_epi<128>(b, ta, tb, stream);
-    case 192: return dispatch_epi<192>(b, ta, tb, stream);
-    case 224: return dispatch_epi<224>(b, ta, tb, stream);
-    case 256: return dispatch_epi<256>(b, ta, tb, stream);
+    case 64: return dispatch_epi<64, false>(a, ta, tb, stream);
+    case 128: return dispatch_epi<128, false>(a, ta, tb, stream);
+    case 192: return dispatch_epi<192, false>(a, ta, tb, stream);
+    case 224: return dispatch_epi<224, false>(a, ta, tb, stream);
+    case 256: return dispatch_epi<256, false>(a, ta, tb, stream);
   }
   return set_error(WVN_ERR_INVALID, "gemm: unreachable");
 }
