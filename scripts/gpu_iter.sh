@@ -2,6 +2,11 @@
 # iteration script (rewritten per experiment)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-WVN_GEMM_PAIR=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_kernel --launch-skip 5 --launch-count 1 -f -o gpurun_out/gemm_fc1 python scripts/gemm_timing.py 2>&1 | tail -5
-WVN_GEMM_PAIR=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_kernel --launch-skip 11 --launch-count 1 -f -o gpurun_out/gemm_proj python scripts/gemm_timing.py 2>&1 | tail -3
-ls -la gpurun_out/*.ncu-rep
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 600 python bench.py --steps 5 --warmup 3 --cpu-frames 0 2> gpurun_out/bench_iter.err | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); r = d['roofline']
+        print('fps', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'attn TF', round(r['achieved'],1), 'attn share', round(r['share_of_step'],3), 'gemm share', round(r['gemm_share_of_step'],3))
+"

@@ -47,9 +47,6 @@ struct GemmArgs {
   float cg_std_factor = 0.5f;
   // launch control
   int max_ctas = 0;             // 0 = one CTA per SM
-  int pair_mode = 0;            // 0 = CTA-pair kernel when the problem is large enough, 1 = force it, -1 = never
-  int b_resident = 0;           // (set by the launcher) pair kernel keeps its half of the weight slab in smem
-  int a_stages = 0;             // (set by the launcher) depth of the pair kernel's operand ring
   int debug = 0;                // debug (-DWVN_GEMM_TIMING builds): 1 = skip the global stores, 2 = skip the epilogue body
   long long* timing = nullptr;  // debug (-DWVN_GEMM_TIMING builds): phase cycle counters of CTA 0
 };

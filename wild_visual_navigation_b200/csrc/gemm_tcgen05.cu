@@ -7,24 +7,20 @@
 // the per-pixel traversability MLP K11): patch-embed, QKV, attention out-proj, MLP fc1/fc2,
 // the STEGO head and the 384->256->32 layers of the traversability MLP.
 //
-// Two kernels share the epilogue:
-//
-// gemm_pair_kernel (the ViT-sized problems) — a CTA PAIR (2-cluster, the two SMs of a TPC) computes a
-//   256 x BN tile with one tcgen05.mma.cta_group::2 stream issued by the leader CTA.  Each CTA stages only
-//   its own 128 rows of A and its own BN/2 rows of W, so per SM the L2 -> smem operand traffic per flop is
-//   (128 + BN/2) / (128 * BN) instead of (128 + BN) / (128 * BN); when K is small (384) each CTA's half of
-//   the [BN, K] weight slab stays RESIDENT in shared memory and the pair walks a contiguous run of m-tiles,
-//   so only activations stream.  These skinny-K GEMMs are bound by the chip-wide L2 -> SM throughput
-//   (~6.3 KB/clk ~= 42 B/clk/SM, measured), not by the tensor pipe: a 128 x 256 single-CTA tile needs
-//   96 B/clk/SM at full MMA rate, the resident pair needs 31.
-//
-// gemm_bf16_kernel (small problems, patch-embed, the row-owner MLP head) — one CTA per SM, 128 x BN tiles.
-//
-// Both: 384 threads, persistent over output tiles,
+// Structure (one CTA per SM, persistent over 128 x BN output tiles, (4 + kEpiWarps) warps):
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
 //   warp 1      : MMA issuer     (single thread issues tcgen05.mma, commits to mbarriers)
 //   warp 2      : TMEM allocator (2 accumulator stages so epilogue(i) overlaps mainloop(i+1))
-//   warps 4..11 : epilogue       (tcgen05.ld -> bias/activation/residual -> global)
+//   warps 4..   : epilogue       (tcgen05.ld -> bias/activation/residual -> global), kEpiWarps / 4 warps per
+//                 TMEM lane quarter.  Measured on B200 (profiles/): with the operands streaming at full rate the
+//                 mainloop alone runs the ViT GEMMs at 1.1-1.6 PFLOP/s; the epilogue is what costs — it is a
+//                 chain of dependent latencies (TMEM load, polynomial GELU, smem transpose, stores), so it is
+//                 spread over many warps (thread-level parallelism hides what 2 warps per scheduler could not).
+//
+// Tried and dropped (git history): a CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x BN tiles, each CTA's
+// half of the weight slab resident in shared memory) — bit-exact, but 5-10 % slower than this kernel at every
+// ViT shape even with the epilogue removed: the mainloop is not bound by L2 -> SM operand traffic.  Also dropped:
+// weight-resident single-CTA tiles, cluster multicast of the weight tile, TMA-store epilogues.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -39,16 +35,23 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
-constexpr int kNumEpiThreads = 256;
+constexpr int kEpiWarps = 16;                 // multiple of 4: kEpiGroups warps share each TMEM lane quarter
+constexpr int kEpiGroups = kEpiWarps / 4;
+constexpr int kNumEpiThreads = kEpiWarps * 32;
+constexpr int kNumThreads = (kEpiWarp0 + kEpiWarps) * 32;
 constexpr int kMaxSmemBytes = 227 * 1024;
-constexpr int kEpiBufBytes = 4096;                            // one 32-row x 128-byte transpose tile
-constexpr int kEpiStageBytes = 8 * kEpiBufBytes;              // one per epilogue warp
-constexpr int kFixedSmemBytes = 1024 /*barriers + scratch*/ + kEpiStageBytes + 1024 /*align slack*/;
 constexpr int kMaxStages = 8;
 
-// Tile enumeration of the single-CTA kernel.  Default: tile ids run n-fastest over the whole (m, n)
+// Per-warp transpose tile of the staged epilogues: 32 rows x 32 columns of the output type.
+__host__ __device__ constexpr int epi_buf_bytes(int epi) {
+  return (epi == EPI_F32 || epi == EPI_RESID_F32) ? 4096 : (epi == EPI_BF16 || epi == EPI_QKV) ? 2048 : 0;
+}
+__host__ __device__ constexpr int fixed_smem_bytes(int epi) {
+  return 1024 /*barriers + scratch*/ + kEpiWarps * epi_buf_bytes(epi) + 1024 /*align slack*/;
+}
+
+// Tile enumeration.  Default: tile ids run n-fastest over the whole (m, n)
 // grid and are dealt round-robin to CTAs (neighbouring CTAs share the A tile through L2).  ROW_OWNER
 // (used by EPI_MLP_HEAD): a CTA owns whole 128-row blocks and visits their n-chunks in order, so
 // per-row reductions across n-chunks stay inside one CTA.
@@ -66,35 +69,16 @@ struct TileIter {
   }
 };
 
-// Work enumeration of the pair kernel: items are (n-block, pair-m-block) with a pair-m-block = 256 rows.
-// Resident weights: the grid is S x num_n pairs; pair p is pinned to n-block p % num_n (its slab is loaded
-// once) and walks the m-blocks slot, slot + S, ... with slot = p / num_n — the num_n pairs of a slot consume
-// the same activation rows at the same time, so those are fetched from HBM once and hit in L2 afterwards.
-// Streaming (large K): items run n-fastest and are dealt round-robin, with the same L2 sharing of A.
-struct PairIter {
-  int lin, end, stride, num_n, n_fixed;
-  bool resident;
-  __device__ PairIter(int num_mp, int nn, bool res) : num_n(nn), n_fixed(0), resident(res) {
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    if (resident) { n_fixed = pair % nn; lin = pair / nn; stride = npairs / nn; end = num_mp; }
-    else { lin = pair; stride = npairs; end = num_mp * nn; }
-  }
-  __device__ bool valid() const { return lin < end; }
-  __device__ void next() { lin += stride; }
-  __device__ int mp() const { return resident ? lin : lin / num_n; }
-  __device__ int n() const { return resident ? n_fixed : lin % num_n; }
-};
-
-template <int BN>
+template <int BN, int EPI>
 struct GemmCfg {
   static constexpr uint32_t kABytes = BM * BK * 2;
   static constexpr uint32_t kBBytes = BN * BK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (kMaxSmemBytes - kFixedSmemBytes) / kStageBytes;
+  static constexpr int kFixed = fixed_smem_bytes(EPI);
+  static constexpr int kStagesRaw = (kMaxSmemBytes - kFixed) / kStageBytes;
   static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
   static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kFixedSmemBytes;
-  static constexpr uint32_t kBHalfBytes = (BN / 2) * BK * 2;  // pair kernel: this CTA's half of a weight k-block
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kFixed;
 };
 
 // GELU(x) = x * Phi(x) with the erf form's Phi.  Phi(-|x|) = 2^p(|x|) (degree-5 minimax fit of log2 Phi(-t) on
@@ -120,17 +104,18 @@ __device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
 
 #define WVN_DBG_STORE && args.debug != 1  // experiment knob ($WVN_GEMM_DEBUG through wvn_gemm_bf16): 1 = no global stores
 
-// One 128 x BN accumulator tile: TMEM -> registers -> bias / activation -> global memory.  Called by the 8 epilogue
-// warps (ewarp 0..7; ewarp & 3 must equal the hardware warp's TMEM lane quarter); m_blk / n_blk locate the tile in C.
+// One 128 x BN accumulator tile: TMEM -> registers -> bias / activation -> global memory.  Called by the kEpiWarps
+// epilogue warps (ewarp & 3 must equal the hardware warp's TMEM lane quarter); the kEpiGroups warps of a lane
+// quarter interleave the tile's 32-column chunks.  m_blk / n_blk locate the tile in C.
 template <int BN, int EPI, int ACT>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32_t tmem_acc, const int m_blk, const int n_blk,
                                               const int ewarp, const int lane, uint8_t* epi_stage, float& head_partial) {
   const int quarter = ewarp & 3;  // TMEM lane quarter this warp may access
-  const int half = ewarp >> 2;    // which interleaved half of the 32-col chunks
+  const int group = ewarp >> 2;   // which of the interleaved 32-col chunk sets
   const int row_in_tile = quarter * 32 + lane;
   const int row = m_blk * BM + row_in_tile;
   const bool row_ok = row < args.M;
-  constexpr int kChunksPerThread = (BN + 63) / 64;
+  constexpr int kChunksPerThread = (BN + 32 * kEpiGroups - 1) / (32 * kEpiGroups);
 
   // Per-row destination bookkeeping
   long long out_row = row;
@@ -145,32 +130,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
   }
 
   if (args.debug == 2) return;  // experiment knob: accumulators are dropped
-  // The TMEM read of chunk i+1 is in flight while chunk i is converted and stored (two register buffers).
-  uint32_t rbuf[2][32];
-  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + half * 32;
-  tmem_ld32(taddr, rbuf[0]);
 #pragma unroll
-  for (int chunk_i = 0; chunk_i < kChunksPerThread; ++chunk_i) {  // the two column-halves interleave 32-col chunks
-    const int c0 = half * 32 + 64 * chunk_i;
+  for (int chunk_i = 0; chunk_i < kChunksPerThread; ++chunk_i) {
+    const int c0 = 32 * (group + kEpiGroups * chunk_i);
     if (c0 >= BN) break;
     const int col0 = n_blk * BN + c0;
-    float4 bv[8];
-    if (args.bias != nullptr) {  // issued ahead of the TMEM wait
-      const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) bv[j] = __ldg(b4 + j);
-    }
+    uint32_t r[32];
+    tmem_ld32(tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c0, r);
     tmem_ld_wait();
-    if (chunk_i + 1 < kChunksPerThread && c0 + 64 < BN) tmem_ld32(taddr + 64 * (chunk_i + 1), rbuf[(chunk_i + 1) & 1]);
-    uint32_t(&r)[32] = rbuf[chunk_i & 1];
     tmem_ld_fence32(r);
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
     if (args.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        v[4 * j + 0] += bv[j].x; v[4 * j + 1] += bv[j].y; v[4 * j + 2] += bv[j].z; v[4 * j + 3] += bv[j].w;
+        const float4 b = __ldg(b4 + j);
+        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
       }
     }
     if (ACT == ACT_RELU) {
@@ -190,38 +167,38 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
     bool qkv_is_v = false;
     if (EPI == EPI_QKV) qkv_is_v = (col0 >= 2 * args.dim);
     if (kStagedEpi && !qkv_is_v) {
-      uint8_t* buf = epi_stage + ewarp * kEpiBufBytes;
+      const uint32_t buf = smem_u32(epi_stage) + ewarp * epi_buf_bytes(EPI);
       const int row_base = m_blk * BM + quarter * 32;
       __syncwarp();  // the previous chunk's read-back is complete
       if (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)  // 128-byte rows: 16-byte chunk q of row r lives at q ^ (r & 7)
-          *reinterpret_cast<float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          sts128(buf + lane * 128 + ((q ^ (lane & 7)) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                 __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
         __syncwarp();
         float* outp = reinterpret_cast<float*>(args.out);
         const int q = lane & 7;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {  // 4 rows x 128 B per instruction
           const int r = it * 4 + (lane >> 3);
-          const float4 val = *reinterpret_cast<const float4*>(buf + r * 128 + ((q ^ (r & 7)) << 4));
+          const uint4 val = lds128(buf + r * 128 + ((q ^ (r & 7)) << 4));
           if (row_base + r < args.M WVN_DBG_STORE) {
             float* dst = outp + static_cast<long long>(row_base + r) * args.ldo + col0 + q * 4;
             if (EPI == EPI_RESID_F32) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val.x), "f"(val.y),
-                           "f"(val.z), "f"(val.w)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(val.x)),
+                           "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w))
                            : "memory");
             } else {
-              *reinterpret_cast<float4*>(dst) = val;
+              *reinterpret_cast<uint4*>(dst) = val;
             }
           }
         }
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q)  // 64-byte rows: chunk q of row r lives at q ^ ((r >> 1) & 3)
-          *reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
-              make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                         pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+          sts128(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), pack_bf16x2(v[8 * q + 0], v[8 * q + 1]),
+                 pack_bf16x2(v[8 * q + 2], v[8 * q + 3]), pack_bf16x2(v[8 * q + 4], v[8 * q + 5]),
+                 pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
         __syncwarp();
         __nv_bfloat16* base;
         long long row_stride, first;
@@ -241,7 +218,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
 #pragma unroll
         for (int it = 0; it < 4; ++it) {  // 8 rows x 64 B per instruction
           const int r = it * 8 + (lane >> 2);
-          const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+          const uint4 val = lds128(buf + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
           if (row_base + r < args.M WVN_DBG_STORE) *reinterpret_cast<uint4*>(base + first + r * row_stride + q * 8) = val;
         }
       }
@@ -307,7 +284,7 @@ template <int BN, int EPI, int ACT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmArgs args) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI>;
   constexpr int STAGES = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -342,7 +319,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], kNumEpiThreads);
+      mbar_init(&acc_empty[i], kEpiWarps);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -406,15 +383,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------------ epilogue
     const int ewarp = warp - kEpiWarp0;
     const int row_in_tile = (ewarp & 3) * 32 + lane;
-    const int half = ewarp >> 2;
+    const int group = ewarp >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     float head_partial = 0.f;
 #ifdef WVN_GEMM_TIMING
     long long e_wait = 0, e_work = 0;
 #endif
-    if (EPI == EPI_MLP_HEAD && half == 0) row_acc[row_in_tile] = 0.f;
-    if (EPI == EPI_MLP_HEAD) asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (EPI == EPI_MLP_HEAD && group == 0) row_acc[row_in_tile] = 0.f;
+    if (EPI == EPI_MLP_HEAD) named_bar_sync(1, kNumEpiThreads);
     for (TileIter<ROW_OWNER> it(num_m, num_n); it.valid(); it.next()) {
 #ifdef WVN_GEMM_TIMING
       long long et0 = clock64();
@@ -426,19 +403,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #endif
       epilogue_tile<BN, EPI, ACT>(args, tmem_base + acc * BN, it.m_blk, it.n_blk, ewarp, lane, epi_stage, head_partial);
       tc_fence_before();
-      mbar_arrive(&acc_empty[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 #ifdef WVN_GEMM_TIMING
       e_wait += et1 - et0; e_work += clock64() - et1;
 #endif
 
       if (EPI == EPI_MLP_HEAD && it.n_blk == num_n - 1) {
-        // combine the two column-halves of each row, then loss_reco -> confidence
+        // combine the column groups of each row, then loss_reco -> confidence
         const int row = it.m_blk * BM + row_in_tile;
         atomicAdd(&row_acc[row_in_tile], head_partial);
         head_partial = 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0) {
+        named_bar_sync(1, kNumEpiThreads);
+        if (group == 0) {
           const float loss = row_acc[row_in_tile] / static_cast<float>(args.feat);
           row_acc[row_in_tile] = 0.f;
           if (row < args.M) {
@@ -452,7 +430,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (args.loss_reco != nullptr) args.loss_reco[row] = loss;
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        named_bar_sync(1, kNumEpiThreads);
       }
     }
 #ifdef WVN_GEMM_TIMING
@@ -468,177 +446,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// CTA-pair kernel: 256 x BN tiles on tcgen05.mma.cta_group::2 (see the file header).
-//   shared memory per CTA:  [ W half-slab (resident: K/64 k-blocks | streaming: ring) ][ A ring ][ barriers ][ epilogue ]
-//   barriers: full[s]   leader only, 1 arrival (its expect_tx) + the bytes of BOTH CTAs' loads
-//             empty[s]  each CTA, signalled by the leader's multicast tcgen05.commit
-//             acc_full  each CTA (multicast commit);  acc_empty  leader only, 16 warp-arrivals (8 per CTA)
-//             b_full    leader only (resident slab landed);  b_empty  each CTA (slab may be overwritten)
-// ------------------------------------------------------------------------------------------------
-template <int BN, int EPI, int ACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmArgs args) {
-  using Cfg = GemmCfg<BN>;
-  const bool resident = args.b_resident != 0;
-  const int STAGES = args.a_stages;
-  const int num_k = args.K / BK;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_b = smem;
-  uint8_t* smem_a = smem + static_cast<uint32_t>(resident ? num_k : STAGES) * Cfg::kBHalfBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + STAGES * Cfg::kABytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kMaxStages;
-  uint64_t* acc_full = bars + 2 * kMaxStages;
-  uint64_t* acc_empty = bars + 2 * kMaxStages + 2;
-  uint64_t* b_full = bars + 2 * kMaxStages + 4;
-  uint64_t* b_empty = bars + 2 * kMaxStages + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int crank = static_cast<int>(cluster_ctarank());
-  const bool leader = crank == 0;
-
-  const int num_m = (args.M + BM - 1) / BM;
-  const int num_mp = (num_m + 1) / 2;
-  const int num_n = args.N / BN;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kMaxStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 16);
-    }
-    mbar_init(b_full, 1);
-    mbar_init(b_empty, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / complete_tx
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0, cur_n = -1;
-      uint32_t phase = 0, be_phase = 0;
-      for (PairIter it(num_mp, num_n, resident); it.valid(); it.next()) {
-        const int mp = it.mp(), n = it.n();
-        const int b_row = n * BN + crank * (BN / 2);
-        if (resident && n != cur_n) {
-          if (cur_n >= 0) { mbar_wait(b_empty, be_phase); be_phase ^= 1; }  // every MMA on the old slab retired
-          if (leader) mbar_arrive_expect_tx(b_full, 2u * static_cast<uint32_t>(num_k) * Cfg::kBHalfBytes);
-          for (int kb = 0; kb < num_k; ++kb)
-            tma_load_2d_pair(&tmap_b, leader_smem_addr(b_full), smem_b + kb * Cfg::kBHalfBytes, kb * BK, b_row);
-          cur_n = n;
-        }
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          const uint32_t full_l = leader_smem_addr(&full_bar[stage]);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * (Cfg::kABytes + (resident ? 0u : Cfg::kBHalfBytes)));
-          tma_load_2d_pair(&tmap_a, full_l, smem_a + stage * Cfg::kABytes, kb * BK, (2 * mp + crank) * BM);
-          if (!resident) tma_load_2d_pair(&tmap_b, full_l, smem_b + stage * Cfg::kBHalfBytes, kb * BK, b_row);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
-      int stage = 0, acc = 0, cur_n = -1;
-      uint32_t phase = 0, acc_phase = 0, bf_phase = 0;
-      WVN_TM_DECL
-      for (PairIter it(num_mp, num_n, resident); it.valid(); it.next()) {
-        const int n = it.n();
-        if (resident && n != cur_n) { mbar_wait(b_full, bf_phase); bf_phase ^= 1; cur_n = n; }
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        WVN_TM(0)
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          WVN_TM(1)
-          const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + (resident ? kb : stage) * Cfg::kBHalfBytes));
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_ss_pair(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair(&empty_bar[stage], 3);  // both CTAs' producers may refill the slot
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          WVN_TM(2)
-        }
-        umma_commit_pair(&acc_full[acc], 3);  // accumulator complete -> both CTAs' epilogues
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        if (resident) {
-          PairIter nx = it;
-          nx.next();
-          if (nx.valid() && nx.n() != n) umma_commit_pair(b_empty, 3);  // slab free once this tile's MMAs retire
-        }
-        WVN_TM_TILE
-      }
-      WVN_TM_FLUSH
-    }
-  } else if (warp >= kEpiWarp0) {
-    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
-    const int ewarp = warp - kEpiWarp0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    float unused = 0.f;
-#ifdef WVN_GEMM_TIMING
-    long long e_wait = 0, e_work = 0;
-#endif
-    for (PairIter it(num_mp, num_n, resident); it.valid(); it.next()) {
-#ifdef WVN_GEMM_TIMING
-      long long et0 = clock64();
-#endif
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
-#ifdef WVN_GEMM_TIMING
-      long long et1 = clock64();
-#endif
-      epilogue_tile<BN, EPI, ACT>(args, tmem_base + acc * BN, 2 * it.mp() + crank, it.n(), ewarp, lane, epi_stage, unused);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(leader_smem_addr(&acc_empty[acc]));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-#ifdef WVN_GEMM_TIMING
-      e_wait += et1 - et0; e_work += clock64() - et1;
-#endif
-    }
-#ifdef WVN_GEMM_TIMING
-    if (args.timing != nullptr && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32) { args.timing[4] = e_wait; args.timing[5] = e_work; }
-#endif
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers / TMEM
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
-  }
-}
-
 template <int BN, int EPI, int ACT>
 int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI>;
+  static_assert(Cfg::kStages >= 2, "tile too wide for the shared-memory budget");
   auto kern = gemm_bf16_kernel<BN, EPI, ACT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -657,100 +468,31 @@ int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
   return WVN_OK;
 }
 
-// Pair-kernel geometry for a [N, K] weight: the half-slab stays resident when it leaves room for
-// at least 4 activation stages.
-struct PairPlan {
-  bool resident;
-  int a_stages;
-  uint32_t smem_bytes;
-};
-
-PairPlan plan_pair(int block_n, int K, bool allow_resident) {
-  const int half = (block_n / 2) * BK * 2;
-  const int slab = (K / BK) * half;
-  const int budget = kMaxSmemBytes - kFixedSmemBytes;
-  PairPlan p;
-  p.resident = allow_resident && slab + 4 * BM * BK * 2 <= budget;
-  p.a_stages = p.resident ? (budget - slab) / (BM * BK * 2) : budget / (BM * BK * 2 + half);
-  if (p.a_stages > kMaxStages) p.a_stages = kMaxStages;
-  p.smem_bytes = static_cast<uint32_t>(p.resident ? slab + p.a_stages * BM * BK * 2 : p.a_stages * (BM * BK * 2 + half)) +
-                 kFixedSmemBytes;
-  return p;
-}
-
-template <int BN, int EPI, int ACT>
-int launch_gemm_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
-  auto kern = gemm_pair_kernel<BN, EPI, ACT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
-    attr_set = true;
-  }
-  const int num_m = (a.M + BM - 1) / BM, num_mp = (num_m + 1) / 2, num_n = a.N / BN;
-  const long long items = static_cast<long long>(num_mp) * num_n;
-  long long pairs = sm_count() / 2;
-  if (a.max_ctas > 0 && a.max_ctas / 2 < pairs) pairs = std::max(1, a.max_ctas / 2);
-  if (pairs > items) pairs = items;
-  PairPlan plan = plan_pair(BN, a.K, true);
-  if (plan.resident) {
-    if (pairs / num_n >= 1) pairs = (pairs / num_n) * num_n;  // S slots x num_n pinned n-blocks
-    else plan = plan_pair(BN, a.K, false);
-  }
-  GemmArgs la = a;
-  la.b_resident = plan.resident ? 1 : 0;
-  la.a_stages = plan.a_stages;
-  if (const char* e = getenv("WVN_GEMM_STAGES")) {  // experiment knob: cap the ring depth
-    const int cap = atoi(e);
-    if (cap >= 2 && cap < la.a_stages) la.a_stages = cap;
-  }
-  prof_begin(PROF_GEMM, stream);
-  kern<<<static_cast<unsigned>(2 * pairs), kNumThreads, plan.smem_bytes, stream>>>(ta, tb, la);
-  prof_end(PROF_GEMM, stream);
-  WVN_CHECK_LAUNCH("gemm_pair_kernel");
-  return WVN_OK;
-}
-
-template <int BN, bool PAIR>
+template <int BN>
 int dispatch_epi(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t s) {
-#define WVN_LAUNCH(E, A)                                            \
-  do {                                                              \
-    if (PAIR) return launch_gemm_pair<BN, E, A>(a, ta, tb, s);      \
-    return launch_gemm<BN, E, A>(a, ta, tb, s);                     \
-  } while (0)
   switch (a.epi) {
     case EPI_BF16:
-      if (a.act == ACT_NONE) WVN_LAUNCH(EPI_BF16, ACT_NONE);
-      if (a.act == ACT_RELU) WVN_LAUNCH(EPI_BF16, ACT_RELU);
-      if (a.act == ACT_GELU) WVN_LAUNCH(EPI_BF16, ACT_GELU);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_BF16, ACT_NONE>(a, ta, tb, s);
+      if (a.act == ACT_RELU) return launch_gemm<BN, EPI_BF16, ACT_RELU>(a, ta, tb, s);
+      if (a.act == ACT_GELU) return launch_gemm<BN, EPI_BF16, ACT_GELU>(a, ta, tb, s);
       break;
     case EPI_F32:
-      if (a.act == ACT_NONE) WVN_LAUNCH(EPI_F32, ACT_NONE);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_F32, ACT_NONE>(a, ta, tb, s);
       break;
     case EPI_RESID_F32:
-      if (a.act == ACT_NONE) WVN_LAUNCH(EPI_RESID_F32, ACT_NONE);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_RESID_F32, ACT_NONE>(a, ta, tb, s);
+      break;
+    case EPI_PATCH:
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_PATCH, ACT_NONE>(a, ta, tb, s);
       break;
     case EPI_QKV:
-      if (a.act == ACT_NONE) WVN_LAUNCH(EPI_QKV, ACT_NONE);
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_QKV, ACT_NONE>(a, ta, tb, s);
       break;
-    case EPI_PATCH:  // single-CTA kernel only (per-row scatter; one small GEMM per frame batch)
-      if (a.act == ACT_NONE && !PAIR) return launch_gemm<BN, EPI_PATCH, ACT_NONE>(a, ta, tb, s);
-      break;
-    case EPI_MLP_HEAD:  // single-CTA kernel only (row-owner tile order)
-      if (a.act == ACT_NONE && !PAIR) return launch_gemm<BN, EPI_MLP_HEAD, ACT_NONE>(a, ta, tb, s);
+    case EPI_MLP_HEAD:
+      if (a.act == ACT_NONE) return launch_gemm<BN, EPI_MLP_HEAD, ACT_NONE>(a, ta, tb, s);
       break;
   }
-#undef WVN_LAUNCH
   return set_error(WVN_ERR_INVALID, "gemm: unsupported epilogue/activation combination (%d, %d)", a.epi, a.act);
-}
-
-// $WVN_GEMM_PAIR=0 forces the single-CTA kernel everywhere (A/B experiments, debugging).
-bool pair_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("WVN_GEMM_PAIR");
-    on = (e != nullptr && atoi(e) == 0) ? 0 : 1;
-  }
-  return on != 0;
 }
 
 }  // namespace
@@ -767,8 +509,7 @@ int pick_block_n(int N) {
 int gemm_bf16(const GemmArgs& a, const void* A, long long lda, const void* W, int block_n, cudaStream_t stream) {
   WVN_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem (M=%d N=%d K=%d)", a.M, a.N, a.K);
   WVN_REQUIRE(a.K % BK == 0, "gemm: K=%d must be a multiple of %d (pad the operands)", a.K, BK);
-  const bool auto_n = block_n == 0;
-  if (auto_n) block_n = pick_block_n(a.N);
+  if (block_n == 0) block_n = pick_block_n(a.N);
   WVN_REQUIRE(block_n == 64 || block_n == 128 || block_n == 192 || block_n == 224 || block_n == 256,
               "gemm: bad block_n %d", block_n);
   WVN_REQUIRE(a.N % block_n == 0, "gemm: N=%d must be a multiple of block_n=%d (pad the weights)", a.N, block_n);
@@ -782,33 +523,15 @@ int gemm_bf16(const GemmArgs& a, const void* A, long long lda, const void* W, in
                 "gemm: bad QKV epilogue geometry (dim=%d heads=%d npad=%d N=%d)", a.dim, a.heads, a.npad, a.N);
   if (a.epi == EPI_F32 || a.epi == EPI_RESID_F32) WVN_REQUIRE(a.ldo % 4 == 0, "gemm: fp32 output pitch must be a multiple of 4");
   if (a.epi == EPI_BF16) WVN_REQUIRE(a.ldo % 8 == 0, "gemm: bf16 output pitch must be a multiple of 8");
-
-  // CTA-pair kernel: whenever the problem has at least one 256-row item per pair of SMs and a pair-capable
-  // tile width (256 / 192 / 128, both halves a whole number of 8-row swizzle groups).
-  int pair_n = 0;
-  if (pair_enabled() && a.pair_mode >= 0 && a.epi != EPI_PATCH && a.epi != EPI_MLP_HEAD) {
-    if (!auto_n) pair_n = (block_n == 256 || block_n == 192 || block_n == 128) ? block_n : 0;
-    else pair_n = a.N % 256 == 0 ? 256 : a.N % 192 == 0 ? 192 : a.N % 128 == 0 ? 128 : 0;
-    const long long items = pair_n ? static_cast<long long>(((a.M + BM - 1) / BM + 1) / 2) * (a.N / pair_n) : 0;
-    if (items < sm_count() / 2 && a.pair_mode <= 0) pair_n = 0;
-  }
   CUtensorMap ta, tb;
   WVN_PROPAGATE(make_tmap_bf16_2d(&ta, A, a.K, a.M, static_cast<uint64_t>(lda) * 2, BK, BM));
-  if (pair_n) {
-    WVN_PROPAGATE(make_tmap_bf16_2d(&tb, W, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, pair_n / 2));
-    switch (pair_n) {
-      case 128: return dispatch_epi<128, true>(a, ta, tb, stream);
-      case 192: return dispatch_epi<192, true>(a, ta, tb, stream);
-      case 256: return dispatch_epi<256, true>(a, ta, tb, stream);
-    }
-  }
   WVN_PROPAGATE(make_tmap_bf16_2d(&tb, W, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, block_n));
   switch (block_n) {
-    case 64: return dispatch_epi<64, false>(a, ta, tb, stream);
-    case 128: return dispatch_epi<128, false>(a, ta, tb, stream);
-    case 192: return dispatch_epi<192, false>(a, ta, tb, stream);
-    case 224: return dispatch_epi<224, false>(a, ta, tb, stream);
-    case 256: return dispatch_epi<256, false>(a, ta, tb, stream);
+    case 64: return dispatch_epi<64>(a, ta, tb, stream);
+    case 128: return dispatch_epi<128>(a, ta, tb, stream);
+    case 192: return dispatch_epi<192>(a, ta, tb, stream);
+    case 224: return dispatch_epi<224>(a, ta, tb, stream);
+    case 256: return dispatch_epi<256>(a, ta, tb, stream);
   }
   return set_error(WVN_ERR_INVALID, "gemm: unreachable");
 }
