@@ -2,8 +2,8 @@
 //
 // Replaces the materialised `softmax(q @ k^T * scale) @ v` of the DINO ViT blocks
 // (SURVEY.md §8 a3 / K4): per (frame, head) the 3137x3137 (ViT-S/8 @448) score matrix is
-// never written to HBM; S lives in tensor memory, P goes through shared memory straight
-// back into the tensor core, O accumulates in tensor memory.
+// never written to HBM; S, P and O all live in tensor memory: P (bf16) is written back with
+// tcgen05.st and consumed by P·V as a TMEM A operand — no shared-memory round trip, no proxy fence.
 //
 // Inputs (written by the QKV GEMM epilogue, bf16):
 //   Q, K : [B*H, npad, 64]   row-major (K-major for the MMA)
@@ -16,7 +16,7 @@
 //   warp 1    : MMA issuer  (S = Q K^T : 4 x UMMA 128x128x16;  O += P V : 8 x UMMA 128x64x16)
 //   warps 2-5 : softmax (1 thread = 1 query row): one tcgen05.ld pass puts the 128 scores of the
 //               row in registers, FMNMX3 row max, lazy rescaling (FA4-style), exp2 on MUFU with an
-//               optional share on the FMA pipe (packed FFMA2 polynomial), P -> bf16 -> swizzled smem,
+//               optional share on the FMA pipe (packed FFMA2 polynomial), P -> bf16 -> TMEM (tcgen05.st),
 //               final O / l epilogue.
 // Measured phase budget per KV tile (clock64, round 1): MUFU issue (1024 clk/warp) is the floor of
 // the softmax phase; the per-tile code path is therefore kept free of mask arithmetic for the 24
@@ -39,19 +39,18 @@ constexpr int kDh = 64;
 constexpr uint32_t kQBytes = kTileQ * kDh * 2;       // 16 KB
 constexpr uint32_t kKBytes = kTileKV * kDh * 2;      // 16 KB
 constexpr uint32_t kVBytes = kDh * kTileKV * 2;      // 16 KB (two 8 KB K-blocks)
-constexpr uint32_t kPBytes = kTileQ * kTileKV * 2;   // 32 KB (two 16 KB K-blocks)
-constexpr int kStages = 2;
+constexpr int kStages = 2;  // K / V^T ring depth (3 fits twice per SM now that P lives in TMEM; measured: no gain)
 constexpr uint32_t kOffQ = 0;
 constexpr uint32_t kOffK = kOffQ + kQBytes;
 constexpr uint32_t kOffV = kOffK + kStages * kKBytes;
-constexpr uint32_t kOffP = kOffV + kStages * kVBytes;
-constexpr uint32_t kOffBar = kOffP + kPBytes;
+constexpr uint32_t kOffBar = kOffV + kStages * kVBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 256;
-constexpr uint32_t kTmemCols = 256;  // S: [0,128)  O: [128,192)
+constexpr uint32_t kTmemCols = 256;  // S: [0,128)  O: [128,192)  P (bf16 pairs): [192,256)
 constexpr uint32_t kColS = 0;
 constexpr uint32_t kColO = 128;
+constexpr uint32_t kColP = 192;
 constexpr float kRescaleThreshold = 8.0f;  // in log2 units (FA4-style lazy rescale)
-constexpr int kDefaultPoly = 0;            // software-exp2 share: pairs out of every 4 pairs (see poly_exp2_pair)
+constexpr int kDefaultPoly = 1;            // software-exp2 share: pairs out of every 4 pairs (see poly_exp2_pair)
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -87,9 +86,7 @@ __device__ __forceinline__ void poly_exp2_pair(uint64_t x2, float& e0, float& e1
 
 // Per-thread softmax state and the shared-memory / tensor-memory handles one row needs.
 struct SoftmaxCtx {
-  uint32_t tmem_s, tmem_o;
-  uint8_t* p_row;
-  int sw;
+  uint32_t tmem_s, tmem_o, tmem_p;
   float sl2;
   uint64_t *s_full, *s_free, *p_full, *pv_done;
   float m_ref, l;
@@ -185,7 +182,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& c, int j, int valid, lo
           e1 = fast_exp2(x1);
         }
         if ((i >> 1) & 1) lb = add2(lb, pack2(e0, e1)); else la = add2(la, pack2(e0, e1));
-        sr[q][i >> 1] = pack_bf16x2(e0, e1);  // packed bf16 pairs overwrite the consumed scores
+        sr[q >> 1][(q & 1) * 16 + (i >> 1)] = pack_bf16x2(e0, e1);  // packed pairs overwrite consumed scores: P columns [0,64)
       }
     }
     float s0, s1;
@@ -200,7 +197,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& c, int j, int valid, lo
         const float e0 = (col < valid) ? fast_exp2(fmaf(__uint_as_float(sr[q][i]), c.sl2, -mb)) : 0.f;
         const float e1 = (col + 1 < valid) ? fast_exp2(fmaf(__uint_as_float(sr[q][i + 1]), c.sl2, -mb)) : 0.f;
         c.l += e0 + e1;
-        sr[q][i >> 1] = pack_bf16x2(e0, e1);
+        sr[q >> 1][(q & 1) * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
       }
     }
   }
@@ -208,18 +205,12 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& c, int j, int valid, lo
 
   if (j > 0 && !waited_pv) mbar_wait(c.pv_done, (j - 1) & 1);  // P buffer free again (PV(j-1) retired)
   WVN_TPH(3)
-  // ---- P -> swizzled smem: 32 columns = 4 x 16-byte chunks of K-block (q >> 1), chunk (q & 1) * 4 + t
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint8_t* blk = c.p_row + (q >> 1) * (kPBytes / 2);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int chunk = ((q & 1) * 4 + t) ^ c.sw;
-      *reinterpret_cast<uint4*>(blk + chunk * 16) =
-          make_uint4(sr[q][4 * t + 0], sr[q][4 * t + 1], sr[q][4 * t + 2], sr[q][4 * t + 3]);
-    }
-  }
-  fence_proxy_async_smem();   // P(j) visible to the tensor core (async proxy)
+  // ---- P -> tensor memory (the A operand of P·V is read from TMEM: no shared-memory round trip, no
+  // generic->async proxy fence): row = lane, 64 columns of packed bf16 pairs
+  tmem_st32(c.tmem_p, sr[0]);
+  tmem_st32(c.tmem_p + 32, sr[1]);
+  tmem_st_wait();
+  tc_fence_before();
   mbar_arrive(c.p_full);
   WVN_TPH(4)
 #undef WVN_TPH
@@ -232,15 +223,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* k_empty = bars + 3;  // [2]
-  uint64_t* v_full = bars + 5;   // [2]
-  uint64_t* v_empty = bars + 7;  // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* s_free = bars + 10;
-  uint64_t* p_full = bars + 11;
-  uint64_t* pv_done = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* k_full = bars + 1;                 // [kStages]
+  uint64_t* k_empty = k_full + kStages;        // [kStages]
+  uint64_t* v_full = k_empty + kStages;        // [kStages]
+  uint64_t* v_empty = v_full + kStages;        // [kStages]
+  uint64_t* s_full = v_empty + kStages;
+  uint64_t* s_free = s_full + 1;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* pv_done = s_full + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -282,8 +273,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_arrive_expect_tx(q_full, kQBytes);
       tma_load_2d(&tmap_q, q_full, smem + kOffQ, 0, row0 + q_tile * kTileQ);
       for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = j % kStages;
+        const uint32_t ph = (j / kStages) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[st], kKBytes);
         tma_load_2d(&tmap_k, &k_full[st], smem + kOffK + st * kKBytes, 0, row0 + j * kTileKV);
@@ -303,8 +294,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const uint64_t desc_q = make_sw128_kmajor_desc(smem_u32(smem + kOffQ));
 
       auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = j % kStages;
+        const uint32_t ph = (j / kStages) & 1;
         mbar_wait(&k_full[st], ph);
         if (j > 0) mbar_wait(s_free, (j - 1) & 1);  // softmax has drained S(j-1) from TMEM
         tc_fence_after();
@@ -333,19 +324,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         WVN_TM(3)
         if (j + 1 < nkv) issue_qk(j + 1);  // overlaps softmax(j)'s tail and P(j) hand-off
         WVN_TM(0)
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = j % kStages;
+        const uint32_t ph = (j / kStages) & 1;
         mbar_wait(p_full, j & 1);
         WVN_TM(1)
         mbar_wait(&v_full[st], ph);
         tc_fence_after();
-        const uint32_t p_addr = smem_u32(smem + kOffP);
         const uint32_t v_addr = smem_u32(smem + kOffV + st * kVBytes);
 #pragma unroll
         for (int ks = 0; ks < kTileKV / 16; ++ks) {
-          const uint64_t desc_p = make_sw128_kmajor_desc(p_addr + (ks >> 2) * (kPBytes / 2)) + 2 * (ks & 3);
           const uint64_t desc_v = make_sw128_kmajor_desc(v_addr + (ks >> 2) * (kVBytes / 2)) + 2 * (ks & 3);
-          umma_bf16_ss(tmem_o, desc_p, desc_v, idesc_o, (j | ks) != 0);
+          umma_bf16_ts(tmem_o, tmem_base + kColP + 8 * ks, desc_v, idesc_o, (j | ks) != 0);
         }
         umma_commit(&v_empty[st]);
         umma_commit(pv_done);
@@ -363,8 +352,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     SoftmaxCtx c;
     c.tmem_s = tmem_base + lane_base + kColS;
     c.tmem_o = tmem_base + lane_base + kColO;
-    c.p_row = smem + kOffP + row * 128;
-    c.sw = row & 7;
+    c.tmem_p = tmem_base + lane_base + kColP;
     c.sl2 = args.scale_log2;
     c.s_full = s_full; c.s_free = s_free; c.p_full = p_full; c.pv_done = pv_done;
     c.m_ref = -INFINITY;  // running reference max (raw score units)

@@ -230,6 +230,20 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (bf16, K-major) is read from tensor memory — lane = row,
+// each 32-bit column holds two consecutive K elements, so one K=16 step spans 8 columns.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Arrive (count 1) on an mbarrier once every previously issued tcgen05.mma of this thread
 // has completed.  Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
