@@ -705,7 +705,23 @@ int wvn_mlp_infer_pixels(wvn_mlp_infer_t* h, const float* tokens, int batch, int
       a.sy = static_cast<float>(gh - 1) / static_cast<float>(out_h - 1);
       a.sx = static_cast<float>(gw - 1) / static_cast<float>(out_w - 1);
       a.ww = ww; a.feat = h->dim;
+#ifdef WVN_GEMM_TIMING
+      static long long* ptb = nullptr;
+      if (!ptb) cudaMalloc(&ptb, 16 * sizeof(long long));
+      a.timing = ptb;
+#endif
       WVN_PROPAGATE(pixel_head(a, h->w2.p, h->h1_p, s));
+#ifdef WVN_GEMM_TIMING
+      {
+        long long t[16];
+        cudaMemcpyAsync(t, ptb, sizeof(t), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        const long long n = t[5] > 0 ? t[5] : 1;
+        fprintf(stderr, "[pixel_head timing, cycles per tile of CTA 0 (%lld tiles)] phaseA+sync %lld  phaseB+sync %lld  mma_wait %lld  "
+                "epilogue %lld  end_sync %lld | producer: tables+bar %lld  copy %lld  pix/gram %lld\n", n, t[0] / n, t[1] / n, t[2] / n, t[3] / n,
+                t[4] / n, t[8] / n, t[9] / n, t[10] / n);
+      }
+#endif
     }
     return WVN_OK;
   }

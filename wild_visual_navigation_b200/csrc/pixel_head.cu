@@ -39,9 +39,19 @@ constexpr uint32_t kOffA = 0;                      // [4 K-blocks][128 rows][128
 constexpr uint32_t kOffW2 = 65536;                 // [4 K-blocks][32 rows][128 B]
 constexpr uint32_t kOffGv = kOffW2 + 16384;        // [2][kWinMax][kGvStride] fp32
 constexpr uint32_t kOffN2 = kOffGv + 2 * kWinMax * kGvStride * 4;  // [2][kWinMax][2] fp32: |xv|^2, xv_c.xv_{c+1}
-constexpr uint32_t kOffConst = kOffN2 + 2 * kWinMax * 2 * 4;      // packed constants (see PixelHeadConsts)
-constexpr uint32_t kOffBar = kOffConst + sizeof(PixelHeadConsts);
+constexpr uint32_t kOffPix = kOffN2 + 2 * kWinMax * 2 * 4;        // per-tile pixel tables (see PixTables)
+struct PixTables {
+  float wx[kTileW];         // horizontal blend weight of pixel px
+  int c0[kTileW];           // its left window column (token column - cx0)
+  int start[kWinMax + 2];   // first pixel of each window cell (kTileW for cells with no pixel)
+  int row0[kTileH * kWinMax], row1[kTileH * kWinMax];  // element offsets of the upper / lower source token row of window cell (r, c)
+};
+constexpr uint32_t kOffBar = kOffPix + ((sizeof(PixTables) + 15) / 16) * 16;
 constexpr uint32_t kSmemBytes = kOffBar + 64;
+
+// Weight-only constants of the head (2 * R^T c, R^T R, b2, ...): read as constant-bank operands of the
+// epilogue's FMAs.  Copied device-to-device on the launch stream before every launch (pixel_head()).
+__constant__ PixelHeadConsts c_ph;
 
 __device__ __forceinline__ void ac_true(int dst, float scale, int in_size, int& i0, float& w1) {
   const float s = dst * scale;
@@ -49,12 +59,19 @@ __device__ __forceinline__ void ac_true(int dst, float scale, int in_size, int& 
   w1 = s - static_cast<float>(i0);
 }
 
+// max(x, 0) fused into the bf16x2 conversion
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 pixel_head_kernel(const __grid_constant__ CUtensorMap tmap_w2, const PixelHeadArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* gv = reinterpret_cast<float*>(smem + kOffGv);
   float* n2 = reinterpret_cast<float*>(smem + kOffN2);
-  PixelHeadConsts* cs = reinterpret_cast<PixelHeadConsts*>(smem + kOffConst);
+  PixTables* pt = reinterpret_cast<PixTables*>(smem + kOffPix);
   uint64_t* w2_full = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* mma_done = w2_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w2_full + 2);
@@ -64,6 +81,7 @@ pixel_head_kernel(const __grid_constant__ CUtensorMap tmap_w2, const PixelHeadAr
   const long long tiles_per_frame = static_cast<long long>(tiles_x) * tiles_y;
   const long long num_tiles = tiles_per_frame * a.batch;
   const int P = a.gh * a.gw;
+  const int ww = a.ww;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) { printf("[wvn] pixel_head: smem base not 1024B aligned\n"); __trap(); }
@@ -71,8 +89,6 @@ pixel_head_kernel(const __grid_constant__ CUtensorMap tmap_w2, const PixelHeadAr
     mbar_init(mma_done, 1);
     fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < static_cast<int>(sizeof(PixelHeadConsts) / 4); i += kThreads)
-    reinterpret_cast<float*>(cs)[i] = reinterpret_cast<const float*>(a.consts)[i];
   if (warp == 0) tmem_alloc(tmem_slot, 32);
   tc_fence_before();
   __syncthreads();
@@ -83,180 +99,235 @@ pixel_head_kernel(const __grid_constant__ CUtensorMap tmap_w2, const PixelHeadAr
     for (int kb = 0; kb < 4; ++kb) tma_load_2d(&tmap_w2, w2_full, smem + kOffW2 + kb * 4096, kb * 64, 0);
   }
 
-  uint32_t mma_phase = 0;
-  for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int b = static_cast<int>(tile / tiles_per_frame);
-    const int trem = static_cast<int>(tile - b * tiles_per_frame);
-    const int py0 = (trem / tiles_x) * kTileH, px0 = (trem % tiles_x) * kTileW;
-    int cx0;
+#ifdef WVN_GEMM_TIMING  // phase cycle counters of thread 0 of CTA 0 (debug builds)
+  long long tph[5] = {0, 0, 0, 0, 0}, tprev = clock64(), ntile = 0;
+#define WVN_PH(i) if (threadIdx.x == 0) { const long long tn = clock64(); tph[i] += tn - tprev; tprev = tn; }
+#else
+#define WVN_PH(i)
+#endif
+
+  // Tile geometry: pixel rows [py0, py0+2), pixel columns [px0, px0+64) of frame b; cx0 = first token column of the window.
+  struct TileGeo { int b, py0, px0, cx0; };
+  auto tile_geo = [&](long long tile) {
+    TileGeo g;
+    g.b = static_cast<int>(tile / tiles_per_frame);
+    const int trem = static_cast<int>(tile - g.b * tiles_per_frame);
+    g.py0 = (trem / tiles_x) * kTileH;
+    g.px0 = (trem % tiles_x) * kTileW;
     float tmpw;
-    ac_true(px0, a.sx, a.gw, cx0, tmpw);
-    const float* gub = a.gu + static_cast<long long>(b) * P * a.ldg;
+    ac_true(g.px0, a.sx, a.gw, g.cx0, tmpw);
+    return g;
+  };
 
-    // ---------------- phase A: vertical blend of the token window (G | U | cT) + |x|^2 ingredients
-    {
-      // all global loads of this thread are issued before any is consumed (one L2 latency per tile, not one
-      // per loop trip): at most kTileH * kWinMax * 73 / 256 = 6 float4 pairs per thread
-      constexpr int kMaxIt = (kTileH * kWinMax * (kGvStride / 4) + kThreads - 1) / kThreads;
-      const int n_items = kTileH * a.ww * (kGvStride / 4);
-      float4 g0[kMaxIt], g1[kMaxIt];
-      float wys[kMaxIt];
+  // ---------------- phase A (warps 4-7, one tile AHEAD of the consumers): vertical blend of the token window
+  // (G | U | cT) into gv, the |x|^2 ingredients into n2, and the per-pixel horizontal tables.
+#ifdef WVN_GEMM_TIMING
+  long long pph[4] = {0, 0, 0, 0}, pprev = 0;
+#define WVN_PP0 if (threadIdx.x == 128) pprev = clock64();
+#define WVN_PP(i) if (threadIdx.x == 128) { const long long tn = clock64(); pph[i] += tn - pprev; pprev = tn; }
+#else
+#define WVN_PP0
+#define WVN_PP(i)
+#endif
+  auto phase_a = [&](const TileGeo& g) {
+    const int t = threadIdx.x - 128;  // 0..127
+    WVN_PP0
+    const float* gub = a.gu + static_cast<long long>(g.b) * P * a.ldg;
+    int y0r[kTileH], y1r[kTileH];
+    float wyr[kTileH];
 #pragma unroll
-      for (int it = 0; it < kMaxIt; ++it) {
-        const int i = threadIdx.x + it * kThreads;
-        if (i < n_items) {
-          const int v4 = i % (kGvStride / 4);
-          const int c = (i / (kGvStride / 4)) % a.ww;
-          const int r = i / ((kGvStride / 4) * a.ww);
-          int y0;
-          ac_true(py0 + r, a.sy, a.gh, y0, wys[it]);
-          const int y1 = min(y0 + 1, a.gh - 1);
-          const int tc = min(cx0 + c, a.gw - 1);
-          g0[it] = __ldg(reinterpret_cast<const float4*>(gub + (static_cast<long long>(y0) * a.gw + tc) * a.ldg) + v4);
-          g1[it] = __ldg(reinterpret_cast<const float4*>(gub + (static_cast<long long>(y1) * a.gw + tc) * a.ldg) + v4);
+    for (int r = 0; r < kTileH; ++r) {
+      ac_true(g.py0 + r, a.sy, a.gh, y0r[r], wyr[r]);
+      y1r[r] = min(y0r[r] + 1, a.gh - 1);
+    }
+    // element offsets of the window's source rows: one table entry per (r, c), built by 2 * ww threads, so
+    // that the copy loop below carries no per-item address arithmetic beyond a table lookup
+    if (t < kTileH * ww) {
+      const int r = t >= ww ? 1 : 0, c = t - r * ww;
+      const int tc = min(g.cx0 + c, a.gw - 1);
+      pt->row0[t] = (y0r[r] * a.gw + tc) * static_cast<int>(a.ldg);
+      pt->row1[t] = (y1r[r] * a.gw + tc) * static_cast<int>(a.ldg);
+    }
+    named_bar_sync(2, 128);
+    WVN_PP(0)
+    constexpr int kV4 = kGvStride / 4;
+    constexpr int kBatch = 6;  // float4 pairs in flight per thread and pass (48 registers)
+    const int n_rc = kTileH * ww;
+    // item i = t + 128 * k  <->  (rc, v4) = (i / 73, i % 73), advanced incrementally (128 = 73 + 55)
+    int rc = t >= kV4 ? 1 : 0, v4 = t - rc * kV4;
+    while (rc < n_rc) {
+      float4 g0[kBatch], g1[kBatch];
+      int rcs[kBatch], v4s[kBatch];
+#pragma unroll
+      for (int it = 0; it < kBatch; ++it) {
+        rcs[it] = rc; v4s[it] = v4;
+        if (rc < n_rc) {
+          g0[it] = __ldg(reinterpret_cast<const float4*>(gub + pt->row0[rc]) + v4);
+          g1[it] = __ldg(reinterpret_cast<const float4*>(gub + pt->row1[rc]) + v4);
         }
+        v4 += 128 - kV4; rc += 1;
+        if (v4 >= kV4) { v4 -= kV4; rc += 1; }
       }
 #pragma unroll
-      for (int it = 0; it < kMaxIt; ++it) {
-        const int i = threadIdx.x + it * kThreads;
-        if (i < n_items) {
-          const float wy = wys[it];
+      for (int it = 0; it < kBatch; ++it) {
+        if (rcs[it] < n_rc) {
+          const float wy = wyr[rcs[it] >= ww ? 1 : 0];
           float4 o;
-          o.x = (1.f - wy) * g0[it].x + wy * g1[it].x;
-          o.y = (1.f - wy) * g0[it].y + wy * g1[it].y;
-          o.z = (1.f - wy) * g0[it].z + wy * g1[it].z;
-          o.w = (1.f - wy) * g0[it].w + wy * g1[it].w;
-          reinterpret_cast<float4*>(gv)[i] = o;  // i == (r * ww + c) * (kGvStride / 4) + v4
+          o.x = fmaf(wy, g1[it].x - g0[it].x, g0[it].x);
+          o.y = fmaf(wy, g1[it].y - g0[it].y, g0[it].y);
+          o.z = fmaf(wy, g1[it].z - g0[it].z, g0[it].z);
+          o.w = fmaf(wy, g1[it].w - g0[it].w, g0[it].w);
+          reinterpret_cast<float4*>(gv)[rcs[it] * kV4 + v4s[it]] = o;
         }
       }
     }
-    if (threadIdx.x < kTileH * a.ww) {
+    WVN_PP(1)
+    if (t < kTileW) {  // per-pixel horizontal source column / weight, first pixel of every window cell
+      int x0, xp, xl;
+      float wx, wp;
+      ac_true(g.px0 + t, a.sx, a.gw, x0, wx);
+      pt->wx[t] = wx;
+      pt->c0[t] = x0 - g.cx0;
+      ac_true(g.px0 + t - 1, a.sx, a.gw, xp, wp);
+      if (t == 0 || xp != x0) pt->start[x0 - g.cx0] = t;
+      ac_true(g.px0 + kTileW - 1, a.sx, a.gw, xl, wp);
+      if (t > xl - g.cx0 && t < kWinMax + 2) pt->start[t] = kTileW;  // cells right of the last pixel
+    } else if (t - kTileW < kTileH * ww) {
       // xv_c = (1-wy) t[y0,c] + wy t[y1,c]:  |xv_c|^2 and xv_c . xv_{c+1} from the per-token Gram entries
-      const int c = threadIdx.x % a.ww, r = threadIdx.x / a.ww;
-      int y0;
-      float wy;
-      ac_true(py0 + r, a.sy, a.gh, y0, wy);
-      const bool same_y = (y0 + 1 > a.gh - 1);
-      const int y1 = same_y ? y0 : y0 + 1;
-      const int tc = min(cx0 + c, a.gw - 1);
+      // (0 self, 1 right neighbour, 2 lower neighbour, 3 lower-right, 4 right . lower); all loads unconditional
+      const int q = t - kTileW;
+      const int r = q >= ww ? 1 : 0, c = q - r * ww;
+      const float wy = wyr[r], u = 1.f - wy;
+      const bool same_y = (y0r[r] + 1 > a.gh - 1);
+      const int tc = min(g.cx0 + c, a.gw - 1);
       const bool same_x = (tc + 1 > a.gw - 1);
-      const int tc1 = same_x ? tc : tc + 1;
-      const float* gr = a.gram + static_cast<long long>(b) * P * 5;
-      auto G = [&](int y, int x, int k) { return __ldg(gr + (static_cast<long long>(y) * a.gw + x) * 5 + k); };
-      const float u = 1.f - wy;
-      // K(a,b) lookups: 0 self, 1 right neighbour, 2 lower neighbour, 3 lower-right, 4 (right . lower)
-      const float s00 = G(y0, tc, 0), s10 = G(y1, tc, 0);
-      const float v0 = same_y ? s00 : G(y0, tc, 2);
+      const float* gr = a.gram + static_cast<long long>(g.b) * P * 5;
+      const float* e0 = gr + (static_cast<long long>(y0r[r]) * a.gw + tc) * 5;
+      const float* e1 = gr + (static_cast<long long>(y1r[r]) * a.gw + tc) * 5;
+      const float s00 = __ldg(e0), h0 = __ldg(e0 + 1), v0r = __ldg(e0 + 2), dr = __ldg(e0 + 3), anr = __ldg(e0 + 4);
+      const float s10 = __ldg(e1), h1 = __ldg(e1 + 1);
+      const float v0 = same_y ? s00 : v0r;
       const float nn = u * u * s00 + 2.f * u * wy * v0 + wy * wy * s10;
-      float xx;
-      if (same_x) {
-        xx = nn;
-      } else {
-        const float h0 = G(y0, tc, 1), h1 = G(y1, tc, 1);
-        const float d = same_y ? h0 : G(y0, tc, 3);
-        const float an = same_y ? h0 : G(y0, tc, 4);
-        xx = u * u * h0 + u * wy * (d + an) + wy * wy * h1;
-      }
-      (void)tc1;
-      n2[(r * a.ww + c) * 2 + 0] = nn;
-      n2[(r * a.ww + c) * 2 + 1] = xx;
+      const float d = same_y ? h0 : dr, an = same_y ? h0 : anr;
+      const float xx = same_x ? nn : u * u * h0 + u * wy * (d + an) + wy * wy * h1;
+      n2[(r * ww + c) * 2 + 0] = nn;
+      n2[(r * ww + c) * 2 + 1] = xx;
     }
-    __syncthreads();
+    WVN_PP(2)
+  };
 
-    // ---------------- phase B: horizontal blend -> ReLU -> bf16 -> swizzled A tile (h1)
+  uint32_t mma_phase = 0;
+  if (warp >= 4 && blockIdx.x < num_tiles) phase_a(tile_geo(blockIdx.x));
+  for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const TileGeo g = tile_geo(tile);
+    const int b = g.b, py0 = g.py0, px0 = g.px0, cx0 = g.cx0;
+    __syncthreads();  // phase A of this tile is visible; the previous tile's A operand / accumulator are drained
+    tc_fence_after();
+    WVN_PH(0)
+
+    // ---------------- phase B (all warps): horizontal blend -> ReLU -> bf16 -> swizzled A tile (h1)
     {
-      const int units = kTileH * (a.ww - 1);  // (row, cell) pairs; cell c spans window columns [c, c+1]
+      const int units = kTileH * (ww - 1);  // (row, cell) pairs; cell c spans window columns [c, c+1]
       for (int u = warp; u < units; u += kThreads / 32) {
-        const int r = u / (a.ww - 1), cell = u % (a.ww - 1);
-        // pixels of this row whose left token column is cx0 + cell (a contiguous run)
-        unsigned long long mask = 0ull;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          int x0;
-          float wx;
-          ac_true(px0 + lane + 32 * h, a.sx, a.gw, x0, wx);
-          const unsigned int bal = __ballot_sync(0xffffffffu, x0 - cx0 == cell);
-          mask |= static_cast<unsigned long long>(bal) << (32 * h);
-        }
-        if (mask == 0ull) continue;
-        const float* g0p = gv + (r * a.ww + cell) * kGvStride + 8 * lane;
+        const int r = u >= (ww - 1) ? 1 : 0, cell = u - r * (ww - 1);
+        const int p_begin = pt->start[cell], p_end = pt->start[cell + 1];  // contiguous run of this cell's pixels
+        if (p_begin >= p_end) continue;
+        const float* g0p = gv + (r * ww + cell) * kGvStride + 8 * lane;
         const float4 a0 = reinterpret_cast<const float4*>(g0p)[0], a1 = reinterpret_cast<const float4*>(g0p)[1];
         const float4 b0 = reinterpret_cast<const float4*>(g0p + kGvStride)[0];
         const float4 b1 = reinterpret_cast<const float4*>(g0p + kGvStride)[1];
-        const float g[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float gg[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         const float dg[8] = {b0.x - a0.x, b0.y - a0.y, b0.z - a0.z, b0.w - a0.w,
                              b1.x - a1.x, b1.y - a1.y, b1.z - a1.z, b1.w - a1.w};
-        while (mask) {
-          const int px = __ffsll(static_cast<long long>(mask)) - 1;
-          mask &= mask - 1;
-          int x0;
-          float wx;
-          ac_true(px0 + px, a.sx, a.gw, x0, wx);
-          float h[8];
+        // channel block 8*lane..8*lane+7: K-block lane/8, 16-byte chunk lane%8 (128B swizzle)
+        const uint32_t kb_base = smem_u32(smem + kOffA) + (lane >> 3) * 16384;
+        for (int pxb = p_begin; pxb < p_end; pxb += 3) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) h[i] = fmaxf(fmaf(wx, dg[i], g[i]), 0.f);
-          const int row = r * kTileW + px;
-          // channel block 8*lane..8*lane+7: K-block lane/8, 16-byte chunk lane%8 (128B swizzle)
-          uint8_t* dst = smem + kOffA + (lane >> 3) * 16384 + row * 128 + (((lane & 7) ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]),
-                                                      pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+          for (int k = 0; k < 3; ++k) {  // three independent pixels in flight
+            const int px = pxb + k;
+            if (px < p_end) {
+              const float wx = pt->wx[px];
+              float h[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h[i] = fmaf(wx, dg[i], gg[i]);
+              const int row = r * kTileW + px;
+              sts128(kb_base + row * 128 + (((lane & 7) ^ (row & 7)) << 4), pack_bf16x2_relu(h[0], h[1]),
+                     pack_bf16x2_relu(h[2], h[3]), pack_bf16x2_relu(h[4], h[5]), pack_bf16x2_relu(h[6], h[7]));
+            }
+          }
         }
       }
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    WVN_PH(1)
 
-    // ---------------- layer 2 on the tensor core: D[128, 32] = h1[128, 256] @ W2^T
-    if (threadIdx.x == 128) {  // warp 4 lane 0: not an epilogue warp, so warps 0-3 stay convergent
-      mbar_wait(w2_full, 0);
-      tc_fence_after();
-      constexpr uint32_t idesc = make_idesc_bf16(128, kH2);
+    if (warp >= 4) {
+      // ---------------- layer 2 on the tensor core: D[128, 32] = h1[128, 256] @ W2^T
+      if (threadIdx.x == 128) {
+        mbar_wait(w2_full, 0);
+        tc_fence_after();
+        constexpr uint32_t idesc = make_idesc_bf16(128, kH2);
 #pragma unroll
-      for (int ks = 0; ks < kH1 / 16; ++ks) {
-        const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem + kOffA + (ks >> 2) * 16384)) + 2 * (ks & 3);
-        const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem + kOffW2 + (ks >> 2) * 4096)) + 2 * (ks & 3);
-        umma_bf16_ss(tmem_d, da, db, idesc, ks != 0);
+        for (int ks = 0; ks < kH1 / 16; ++ks) {
+          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem + kOffA + (ks >> 2) * 16384)) + 2 * (ks & 3);
+          const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem + kOffW2 + (ks >> 2) * 4096)) + 2 * (ks & 3);
+          umma_bf16_ss(tmem_d, da, db, idesc, ks != 0);
+        }
+        umma_commit(mma_done);
       }
-      umma_commit(mma_done);
-    }
-
-    // ---------------- epilogue: one thread per pixel (warps 0-3 <-> TMEM lanes 0-127)
-    if (warp < 4) {
+      __syncwarp();
+      // ---------------- producers: once the consumers have taken what they need from gv / n2 / the pixel
+      // tables, build the NEXT tile's while the tensor core and the epilogue work on this one
+      named_bar_sync(1, kThreads);
+      if (tile + gridDim.x < num_tiles) phase_a(tile_geo(tile + gridDim.x));
+    } else {
+      // ---------------- epilogue: one thread per pixel (warps 0-3 <-> TMEM lanes 0-127)
       const int i = threadIdx.x;  // pixel / TMEM lane
       const int r = i >> 6, px = i & 63;
+      const float wx = pt->wx[px];
+      const int c0 = pt->c0[px];
+      const bool same_x = (cx0 + c0 + 1 > a.gw - 1);
+      // U columns of the two neighbouring window columns (c0+1 is a clamped duplicate at the right border)
+      const float4* u0 = reinterpret_cast<const float4*>(gv + (r * ww + c0) * kGvStride + kH1);
+      const float4* u1 = u0 + kGvStride / 4;
+      float ub[kH2 + 4];  // blended U (32) | cT_hi, cT_lo
+#pragma unroll
+      for (int j4 = 0; j4 < kH2 / 4 + 1; ++j4) {
+        const float4 p0 = u0[j4], p1 = u1[j4];
+        ub[4 * j4 + 0] = fmaf(wx, p1.x - p0.x, p0.x);
+        ub[4 * j4 + 1] = fmaf(wx, p1.y - p0.y, p0.y);
+        ub[4 * j4 + 2] = fmaf(wx, p1.z - p0.z, p0.z);
+        ub[4 * j4 + 3] = fmaf(wx, p1.w - p0.w, p0.w);
+      }
+      const float* nn = n2 + (r * ww + c0) * 2;
+      const float ux = 1.f - wx;
+      const float n_c1 = same_x ? nn[0] : nn[2];
+      const float xx = same_x ? nn[0] : nn[1];
+      const float gram = ux * ux * nn[0] + 2.f * ux * wx * xx + wx * wx * n_c1;
+      asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");  // gv / n2 / tables consumed: producers may refill
+
       mbar_wait(mma_done, mma_phase);
       tc_fence_after();
+      WVN_PH(2)
       uint32_t raw[32];
       tmem_ld32(tmem_d + (static_cast<uint32_t>(warp * 32) << 16), raw);
       tmem_ld_wait();
       float h2[kH2];
 #pragma unroll
-      for (int j = 0; j < kH2; ++j) h2[j] = fmaxf(__uint_as_float(raw[j]) + cs->b2[j], 0.f);
-      int x0;
-      float wx;
-      ac_true(px0 + px, a.sx, a.gw, x0, wx);
-      const int c0 = x0 - cx0;
-      const bool same_x = (x0 + 1 > a.gw - 1);
-      const float* u0 = gv + (r * a.ww + c0) * kGvStride + kH1;
-      const float* u1 = u0 + kGvStride;  // window column c0+1 (a clamped duplicate at the right border)
+      for (int j = 0; j < kH2; ++j) h2[j] = fmaxf(__uint_as_float(raw[j]) + c_ph.b2[j], 0.f);
       // traversability logit, |r|^2 quadratic form (upper-triangular M with doubled off-diagonals), r.x
-      float t = cs->b0, q = cs->cc, cross = 0.f;
+      float t = c_ph.b0, q = c_ph.cc, cross = ub[kH2] + ub[kH2 + 1];
 #pragma unroll
       for (int j = 0; j < kH2; ++j) {
-        t = fmaf(cs->w0[j], h2[j], t);
-        float acc = cs->tv[j];
+        t = fmaf(c_ph.w0[j], h2[j], t);
+        float acc = c_ph.tv[j];
 #pragma unroll
-        for (int k = j; k < kH2; ++k) acc = fmaf(cs->m[j * kH2 + k], h2[k], acc);
+        for (int k = j; k < kH2; ++k) acc = fmaf(c_ph.m[j * kH2 + k], h2[k], acc);
         q = fmaf(h2[j], acc, q);
-        cross = fmaf(h2[j], fmaf(wx, u1[j] - u0[j], u0[j]), cross);
+        cross = fmaf(h2[j], ub[j], cross);
       }
-      cross += fmaf(wx, (u1[kH2] + u1[kH2 + 1]) - (u0[kH2] + u0[kH2 + 1]), u0[kH2] + u0[kH2 + 1]);
-      const float* nn = n2 + (r * a.ww + c0) * 2;
-      const float ux = 1.f - wx;
-      const float n_c1 = same_x ? nn[0] : nn[2];
-      const float xx = same_x ? nn[0] : nn[1];
-      const float gram = ux * ux * nn[0] + 2.f * ux * wx * xx + wx * wx * n_c1;
       const float loss = fmaxf(q - 2.f * cross + gram, 0.f) / static_cast<float>(a.feat);
       const float mean = __ldg(a.cg_mean), sd = __ldg(a.cg_std);
       const float shifted = mean + sd * a.std_factor;
@@ -267,11 +338,22 @@ pixel_head_kernel(const __grid_constant__ CUtensorMap tmap_w2, const PixelHeadAr
       a.conf[o] = 1.f - (xc - lo) / (hi - lo);
       if (a.loss_reco != nullptr) a.loss_reco[o] = loss;
       tc_fence_before();
+      WVN_PH(3)
     }
     mma_phase ^= 1;
-    __syncthreads();  // A tile, Gv and the accumulator may be overwritten by the next tile
-    tc_fence_after();
+#ifdef WVN_GEMM_TIMING
+    ++ntile;
+#endif
   }
+#ifdef WVN_GEMM_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.timing != nullptr) {
+    for (int i = 0; i < 5; ++i) a.timing[i] = tph[i];
+    a.timing[5] = ntile;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 128 && a.timing != nullptr)
+    for (int i = 0; i < 3; ++i) a.timing[8 + i] = pph[i];
+#endif
+#undef WVN_PH
 
   tc_fence_before();
   __syncthreads();
@@ -396,6 +478,7 @@ int token_gram(const void* tok_bf16, float* gram, int batch, int gh, int gw, int
 int pixel_head(const PixelHeadArgs& a, const void* w2_bf16, int w2_ld, cudaStream_t stream) {
   WVN_REQUIRE(a.ww >= 2 && a.ww <= kWinMax && a.W % kTileW == 0 && a.H % kTileH == 0, "pixel_head: unsupported geometry");
   WVN_REQUIRE(a.ldg >= kGvStride && a.ldg % 4 == 0, "pixel_head: ldg %lld too small", a.ldg);
+  WVN_REQUIRE(static_cast<long long>(a.gh) * a.gw * a.ldg < (1ll << 31), "pixel_head: token grid too large for 32-bit row offsets");
   CUtensorMap tw;
   WVN_PROPAGATE(make_tmap_bf16_2d(&tw, w2_bf16, kH1, kH2, static_cast<uint64_t>(w2_ld) * 2, 64, kH2));
   static bool attr_set = false;
@@ -405,6 +488,7 @@ int pixel_head(const PixelHeadArgs& a, const void* w2_bf16, int w2_ld, cudaStrea
   }
   const long long tiles = static_cast<long long>(a.batch) * (a.H / kTileH) * (a.W / kTileW);
   int grid = static_cast<int>(std::min<long long>(tiles, static_cast<long long>(sm_count()) * 2));
+  WVN_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_ph, a.consts, sizeof(PixelHeadConsts), 0, cudaMemcpyDeviceToDevice, stream));
   pixel_head_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tw, a);
   WVN_CHECK_LAUNCH("pixel_head_kernel");
   return WVN_OK;

@@ -35,6 +35,7 @@ struct PixelHeadArgs {
   float sy = 0.f, sx = 0.f;      // (gh-1)/(H-1), (gw-1)/(W-1)
   int ww = 0;                    // token-window columns per tile (from pixel_head_supported)
   int feat = 0;                  // D
+  long long* timing = nullptr;   // debug (-DWVN_GEMM_TIMING builds): phase cycle counters of CTA 0
 };
 
 // Returns the token-window width if the fused kernel supports this geometry, else 0.
