@@ -361,6 +361,12 @@ int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_
       if (sub_env < 1) sub_env = 1 << 30;
     }
     const int sub = std::min(sub_env, nb);
+    // "Snake" order: every kernel of the chain walks its rows in the opposite direction to its producer, so it
+    // starts on the rows that were written last and are still in the 126 MB L2 ($WVN_VIT_SNAKE=0 disables).
+    static int snake = -1;
+    if (snake < 0) { const char* e = getenv("WVN_VIT_SNAKE"); snake = (e && atoi(e) == 0) ? 0 : 1; }
+    int dir = 0;  // the patch-embed GEMM above ran first-to-last
+    auto next_dir = [&]() { dir = snake ? dir ^ 1 : 0; return dir; };
     __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(h->xn.p);
     __nv_bfloat16* attn = reinterpret_cast<__nv_bfloat16*>(h->attn.p);
     for (int l = 0; l < c.depth; ++l) {
@@ -370,6 +376,7 @@ int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_
         const long long roff = static_cast<long long>(s0) * h->npad;
         LayerNormArgs ls = la;
         ls.rows = static_cast<long long>(ns) * h->npad;
+        ls.reverse = next_dir();
         WVN_PROPAGATE(layernorm_rows(x + roff * D, h->wp<float>(b + "norm1.weight"), h->wp<float>(b + "norm1.bias"),
                                      xn + roff * D, nullptr, ls, s));
         GemmArgs g;
@@ -379,6 +386,7 @@ int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_
         g.q = reinterpret_cast<__nv_bfloat16*>(h->q.p) + hoff;
         g.k = reinterpret_cast<__nv_bfloat16*>(h->k.p) + hoff;
         g.vt = reinterpret_cast<__nv_bfloat16*>(h->vt.p) + hoff;
+        g.reverse_m = next_dir();
         WVN_PROPAGATE(gemm_bf16(g, xn + roff * D, D, h->wp<void>(b + "attn.qkv.weight"), 0, s));
       }
       {
@@ -386,6 +394,7 @@ int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_
         a.batch = nb; a.heads = c.heads; a.npad = h->npad; a.n_valid = h->n_valid;
         a.scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim 64: 64^-0.5 * log2(e)
         a.out = h->attn.p; a.ldo = D;
+        a.reverse = next_dir();
         WVN_PROPAGATE(attention_bf16(a, h->q.p, h->k.p, h->vt.p, s));
       }
       for (int s0 = 0; s0 < nb; s0 += sub) {
@@ -398,26 +407,31 @@ int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_
           GemmArgs g;
           g.M = srows; g.N = D; g.K = D; g.epi = EPI_RESID_F32; g.bias = h->wp<float>(b + "attn.proj.bias");
           g.out = x + roff * D; g.ldo = D;
+          g.reverse_m = next_dir();
           WVN_PROPAGATE(gemm_bf16(g, attn + roff * D, D, h->wp<void>(b + "attn.proj.weight"), 0, s));
         }
+        ls.reverse = next_dir();
         WVN_PROPAGATE(layernorm_rows(x + roff * D, h->wp<float>(b + "norm2.weight"), h->wp<float>(b + "norm2.bias"),
                                      xn + roff * D, nullptr, ls, s));
         {
           GemmArgs g;
           g.M = srows; g.N = c.mlp_dim; g.K = D; g.epi = EPI_BF16; g.act = ACT_GELU;
           g.bias = h->wp<float>(b + "mlp.fc1.bias"); g.out = h->hid.p; g.ldo = c.mlp_dim;  // hid is reused per sub-chunk
+          g.reverse_m = next_dir();
           WVN_PROPAGATE(gemm_bf16(g, xn + roff * D, D, h->wp<void>(b + "mlp.fc1.weight"), 0, s));
         }
         {
           GemmArgs g;
           g.M = srows; g.N = D; g.K = c.mlp_dim; g.epi = EPI_RESID_F32; g.bias = h->wp<float>(b + "mlp.fc2.bias");
           g.out = x + roff * D; g.ldo = D;
+          g.reverse_m = next_dir();
           WVN_PROPAGATE(gemm_bf16(g, h->hid.p, c.mlp_dim, h->wp<void>(b + "mlp.fc2.weight"), 0, s));
         }
       }
     }
     __nv_bfloat16* tok_bf = reinterpret_cast<__nv_bfloat16*>(h->tok_bf16.p) + static_cast<long long>(b0) * h->npad * D;
     float* tok_f = tokens_out ? tokens_out + static_cast<long long>(b0) * h->P * D : nullptr;
+    la.reverse = next_dir();
     WVN_PROPAGATE(layernorm_rows(x, h->wp<float>("norm.weight"), h->wp<float>("norm.bias"), tok_bf, tok_f, la, s));
   }
   h->forwarded = true;

@@ -12,6 +12,7 @@ struct AttnArgs {
   float scale_log2 = 0.f;  // head_dim^-0.5 * log2(e)
   void* out = nullptr;     // [batch, npad, ldo] bf16, head h occupies columns [64h, 64h+64)
   long long ldo = 0;
+  int reverse = 0;     // walk (frame, head, q-tile) last-to-first: start on what the QKV GEMM wrote last (L2 hits)
   long long* timing = nullptr;  // debug: 16 cycle counters of block (0,0) (see scripts/bench_attention.py)
 };
 

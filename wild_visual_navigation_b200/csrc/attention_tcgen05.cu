@@ -18,6 +18,8 @@
 //               row in registers, FMNMX3 row max, lazy rescaling (FA4-style), exp2 on MUFU with an
 //               optional share on the FMA pipe (packed FFMA2 polynomial), P -> bf16 -> TMEM (tcgen05.st),
 //               final O / l epilogue.
+// Tried and dropped (git history): two threads per query row (8 softmax warps per CTA, row max agreed
+// through a shared-memory mailbox) — equal to this kernel within noise in the full step.
 // Measured phase budget per KV tile (clock64, round 1): MUFU issue (1024 clk/warp) is the floor of
 // the softmax phase; the per-tile code path is therefore kept free of mask arithmetic for the 24
 // unmasked tiles (the padded last tile runs a separate, masked instantiation — written as separate
@@ -50,7 +52,7 @@ constexpr uint32_t kColS = 0;
 constexpr uint32_t kColO = 128;
 constexpr uint32_t kColP = 192;
 constexpr float kRescaleThreshold = 8.0f;  // in log2 units (FA4-style lazy rescale)
-constexpr int kDefaultPoly = 1;            // software-exp2 share: pairs out of every 4 pairs (see poly_exp2_pair)
+constexpr int kDefaultPoly = 2;            // software-exp2 share: pairs out of every 8 pairs (see poly_exp2_pair)
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -65,7 +67,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 }
 
 // exp2 on the FMA/ALU pipes (Cody-Waite + degree-3 minimax, rel. err 7.5e-5 — well inside the bf16
-// rounding of P): POLY of every 4 element PAIRS are evaluated here instead of on the MUFU unit
+// rounding of P): POLY of every 8 element PAIRS are evaluated here instead of on the MUFU unit
 // (16 ex2/clk/SM), FA4-style.
 __device__ __forceinline__ void poly_exp2_pair(uint64_t x2, float& e0, float& e1) {
   float x0, x1;
@@ -173,7 +175,7 @@ __device__ __forceinline__ void softmax_tile(SoftmaxCtx& c, int j, int valid, lo
         float e0, e1;
         if (POLY == 9) {  // timing experiment only: no exponentials at all (results are wrong)
           unpack2(x2, e0, e1);
-        } else if (((i >> 1) & 3) < POLY) {
+        } else if (((i >> 1) & 7) < POLY) {
           poly_exp2_pair(x2, e0, e1);
         } else {
           float x0, x1;
@@ -235,8 +237,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x;
-  const int bh = blockIdx.y;
+  const int q_tile = args.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int bh = args.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
   const int nkv = args.npad / kTileKV;
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
@@ -417,12 +419,12 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
   WVN_PROPAGATE(make_tmap_bf16_2d(&tq, q, kDh, bh * a.npad, kDh * 2, 64, kTileQ));
   WVN_PROPAGATE(make_tmap_bf16_2d(&tk, k, kDh, bh * a.npad, kDh * 2, 64, kTileKV));
   WVN_PROPAGATE(make_tmap_bf16_2d(&tv, vt, a.npad, bh * kDh, static_cast<uint64_t>(a.npad) * 2, 64, kDh));
-  // share (in quarters) of the exponentials evaluated on the FMA pipe; tuned on B200, overridable
+  // share (in eighths) of the exponentials evaluated on the FMA pipe; tuned on B200, overridable
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("WVN_ATTN_POLY");
     poly = e ? atoi(e) : kDefaultPoly;
-    if ((poly < 0 || poly > 3) && poly != 9) poly = kDefaultPoly;
+    if ((poly < 0 || poly > 4) && poly != 9) poly = kDefaultPoly;
   }
   dim3 grid(a.npad / kTileQ, static_cast<unsigned>(bh));
   auto launch = [&](auto kern) -> int {
@@ -437,6 +439,7 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
     case 1: WVN_PROPAGATE(launch(attention_kernel<1>)); break;
     case 2: WVN_PROPAGATE(launch(attention_kernel<2>)); break;
     case 3: WVN_PROPAGATE(launch(attention_kernel<3>)); break;
+    case 4: WVN_PROPAGATE(launch(attention_kernel<4>)); break;
     default: WVN_PROPAGATE(launch(attention_kernel<9>)); break;
   }
   WVN_CHECK_LAUNCH("attention_kernel");

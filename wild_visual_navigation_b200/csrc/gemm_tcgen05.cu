@@ -335,10 +335,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (TileIter<ROW_OWNER> it(num_m, num_n); it.valid(); it.next()) {
+        const int m_eff = args.reverse_m ? num_m - 1 - it.m_blk : it.m_blk;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * BK, it.m_blk * BM);
+          tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * BK, m_eff * BM);
           tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * BK, it.n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -401,7 +402,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #ifdef WVN_GEMM_TIMING
       long long et1 = clock64();
 #endif
-      epilogue_tile<BN, EPI, ACT>(args, tmem_base + acc * BN, it.m_blk, it.n_blk, ewarp, lane, epi_stage, head_partial);
+      const int m_eff = args.reverse_m ? num_m - 1 - it.m_blk : it.m_blk;
+      epilogue_tile<BN, EPI, ACT>(args, tmem_base + acc * BN, m_eff, it.n_blk, ewarp, lane, epi_stage, head_partial);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -412,7 +414,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
       if (EPI == EPI_MLP_HEAD && it.n_blk == num_n - 1) {
         // combine the column groups of each row, then loss_reco -> confidence
-        const int row = it.m_blk * BM + row_in_tile;
+        const int row = m_eff * BM + row_in_tile;
         atomicAdd(&row_acc[row_in_tile], head_partial);
         head_partial = 0.f;
         named_bar_sync(1, kNumEpiThreads);

@@ -77,7 +77,8 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ gam
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  for (long long row = warp_global; row < a.rows; row += warps_total) {
+  for (long long r = warp_global; r < a.rows; r += warps_total) {
+    const long long row = a.reverse ? a.rows - 1 - r : r;
     const float4* src = reinterpret_cast<const float4*>(x + row * D);
     float4 v[ITERS];
     float s = 0.f;

@@ -22,6 +22,7 @@ struct LayerNormArgs {
   float eps = 1e-6f;
   // only used when an fp32 output is requested (drops CLS + padding rows)
   int npad = 0, n_valid = 0;
+  int reverse = 0;  // walk the rows last-to-first (start where the producer kernel finished: those rows are still in L2)
 };
 
 int image_to_patches(const float* img, void* out_bf16, const ImagePatchArgs& a, cudaStream_t stream);
