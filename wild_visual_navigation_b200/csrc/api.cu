@@ -316,6 +316,8 @@ static int vit_check_loaded(wvn_vit* h, bool need_head) {
   return WVN_OK;
 }
 
+constexpr int kDefaultSubAttn = 1 << 30;  // frames per (LN1, QKV, attention) pass; tuned on B200
+
 int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_w, int resized_h, int resized_w,
                     float* tokens_out, void* stream) {
   WVN_REQUIRE(h && img, "wvn_vit_forward: null argument");
@@ -369,10 +371,19 @@ int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_
     auto next_dir = [&]() { dir = snake ? dir ^ 1 : 0; return dir; };
     __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(h->xn.p);
     __nv_bfloat16* attn = reinterpret_cast<__nv_bfloat16*>(h->attn.p);
+    // The attention half of a block (LN1 -> QKV -> attention) can additionally run over `sub_a` frames at a time
+    // ($WVN_VIT_SUB_ATTN): Q / K / V^T of a half-chunk (118 MB at 16 frames) are consumed while still in L2.
+    static int sub_attn_env = -1;
+    if (sub_attn_env < 0) {
+      const char* e = getenv("WVN_VIT_SUB_ATTN");
+      sub_attn_env = e ? atoi(e) : kDefaultSubAttn;
+      if (sub_attn_env < 1) sub_attn_env = 1 << 30;
+    }
+    const int sub_a = std::min(std::min(sub_attn_env, sub), nb);
     for (int l = 0; l < c.depth; ++l) {
       const std::string b = "blocks." + std::to_string(l) + ".";
-      for (int s0 = 0; s0 < nb; s0 += sub) {
-        const int ns = std::min(sub, nb - s0);
+      for (int s0 = 0; s0 < nb; s0 += sub_a) {
+        const int ns = std::min(sub_a, nb - s0);
         const long long roff = static_cast<long long>(s0) * h->npad;
         LayerNormArgs ls = la;
         ls.rows = static_cast<long long>(ns) * h->npad;
@@ -388,14 +399,12 @@ int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_
         g.vt = reinterpret_cast<__nv_bfloat16*>(h->vt.p) + hoff;
         g.reverse_m = next_dir();
         WVN_PROPAGATE(gemm_bf16(g, xn + roff * D, D, h->wp<void>(b + "attn.qkv.weight"), 0, s));
-      }
-      {
         AttnArgs a;
-        a.batch = nb; a.heads = c.heads; a.npad = h->npad; a.n_valid = h->n_valid;
+        a.batch = ns; a.heads = c.heads; a.npad = h->npad; a.n_valid = h->n_valid;
         a.scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim 64: 64^-0.5 * log2(e)
-        a.out = h->attn.p; a.ldo = D;
+        a.out = attn + roff * D; a.ldo = D;
         a.reverse = next_dir();
-        WVN_PROPAGATE(attention_bf16(a, h->q.p, h->k.p, h->vt.p, s));
+        WVN_PROPAGATE(attention_bf16(a, g.q, g.k, g.vt, s));
       }
       for (int s0 = 0; s0 < nb; s0 += sub) {
         const int ns = std::min(sub, nb - s0);
