@@ -181,7 +181,10 @@ def run_b200(args):
     y_all = torch.where(yv_all, torch.rand(B * smax, generator=g).clamp(min=0.001).to(dev), torch.zeros(B * smax, device=dev))
     row_ids = torch.arange(smax, device=dev)[None, :]
 
-    host_imgs = [t.pin_memory() for t in synthetic_images(3, B, seed=100 + rank)]
+    frames = synthetic_images(3, B, seed=100 + rank)
+    if args.ingest == "u8":
+        frames = [(t * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous() for t in frames]
+    host_imgs = [t.pin_memory() for t in frames]
     dev_imgs = [t.to(dev) for t in host_imgs]
     host_trav = torch.empty(B, IMG, IMG).pin_memory()
     host_conf = torch.empty(B, IMG, IMG).pin_memory()
@@ -201,7 +204,7 @@ def run_b200(args):
     # device->host, on copy streams so that step k's transfers overlap step k-1 / k+1's compute
     # (double-buffered, exactly what a camera loop around the public API would do).
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    img_buf = [torch.empty(B, 3, IMG, IMG, device=dev) for _ in range(2)]
+    img_buf = [torch.empty_like(host_imgs[0], device=dev) for _ in range(2)]
     out_buf = [(torch.empty(B, IMG, IMG, device=dev), torch.empty(B, IMG, IMG, device=dev), torch.empty(6, device=dev))
                for _ in range(2)]
     ev_in = [torch.cuda.Event() for _ in range(2)]
@@ -316,8 +319,8 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 operands / fp32 accumulate (ViT, STEGO head, per-pixel MLP); fp32 (train step)",
-        "data": "synthetic", "config": workload_config(args, False, B) | {"vit_chunk_frames": args.chunk},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * 3 * IMG * IMG * 4,
+        "data": "synthetic", "config": workload_config(args, False, B) | {"vit_chunk_frames": args.chunk, "ingest": args.ingest},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": host_imgs[0].numel() * host_imgs[0].element_size(),
                 "d2h_bytes_per_step": 2 * B * IMG * IMG * 4 + 24, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -349,6 +352,9 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=32,
                     help="torch CPU threads for the CPU legs (more than ~32 only adds sync overhead on these small ops)")
     ap.add_argument("--profile-only", action="store_true", help="setup + warmup + steps only (for ncu)")
+    ap.add_argument("--ingest", default="f32", choices=["f32", "u8"],
+                    help="frame format at the boundary: f32 = (B,3,H,W) float in [0,1] (the reference's boundary, "
+                         "BASELINE.json); u8 = camera frames (B,H,W,3) uint8, ingest fused into the patch loader (SURVEY.md §8f)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

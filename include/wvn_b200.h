@@ -119,6 +119,15 @@ int wvn_vit_set_weight(wvn_vit_t* h, const char* name, const float* data, long l
 int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_w, int resized_h, int resized_w,
                     float* tokens_out, void* stream);
 
+/* Same, from the camera frame itself: img_hwc [batch, in_h, in_w, 3] uint8 RGB.  Folds into the patch loader the
+ * two steps that precede the interface in the reference's node:
+ *   ros_image_to_torch  — torchvision ToTensor: HWC uint8 -> CHW float / 255   (ros_converter.py:113-126)
+ *   ImageProjector.resize_image — Resize(h, NEAREST) + CenterCrop(h)            (image_projector.py:55-59,199-200)
+ * followed by the interface's own transform as in wvn_vit_forward; with network_input_image_height == image_size
+ * (the shipped configuration) the two NEAREST resizes are one, expressed by resized_h / resized_w. */
+int wvn_vit_forward_u8(wvn_vit_t* h, const unsigned char* img_hwc, int batch, int in_h, int in_w, int resized_h,
+                       int resized_w, float* tokens_out, void* stream);
+
 /* STEGO segmentation head on the tokens of the last forward
  * (stego_interface.py:91-100; [EXTERNAL] stego.stego.Stego.forward / cluster & linear probes):
  *   out[row, :] = head_a(t) + head_b(relu(hidden(t)))           out: [batch*npad, head_out] fp32

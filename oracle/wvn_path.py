@@ -45,6 +45,24 @@ def wvn_transform(img: torch.Tensor, input_size: int) -> torch.Tensor:
     return (img - mean) / std
 
 
+def ros_image_to_float(img_u8_hwc: torch.Tensor) -> torch.Tensor:
+    """``ros_image_to_torch`` (wild_visual_navigation_ros/.../ros_converter.py:113-126): torchvision ``ToTensor`` on
+    the decoded rgb8 frame — (B,H,W,3) uint8 -> (B,3,H,W) float32 = value / 255."""
+    return img_u8_hwc.permute(0, 3, 1, 2).to(torch.float32).div(255)
+
+
+def resize_image(img: torch.Tensor, new_h: int) -> torch.Tensor:
+    """``ImageProjector.resize_image`` for the square configuration (image_projector.py:55-59,199-200):
+    ``T.Compose([T.Resize(new_h, NEAREST), T.CenterCrop(new_h)])`` on a (B,3,H,W) tensor."""
+    B, C, H, W = img.shape
+    rh, rw = resized_size(H, W, new_h)
+    if (rh, rw) != (H, W):
+        img = F.interpolate(img, size=(rh, rw), mode="nearest")
+    top = int(round((rh - new_h) / 2.0))
+    left = int(round((rw - new_h) / 2.0))
+    return img[:, :, top : top + new_h, left : left + new_h]
+
+
 @torch.no_grad()
 def dino_inference(img: torch.Tensor, sd: dict, cfg: ViTConfig) -> torch.Tensor:
     """``DinoInterface.inference``: transform -> backbone -> bilinear(align_corners=True) to (H, H).

@@ -11,6 +11,7 @@ Fixtures
   mlp_train.pt      reference SimpleMLP + TraversabilityLoss + torch.optim.Adam, 3 steps (small dims)
   mlp_init_384.pt   checksum of the seed-42 init of the real-size SimpleMLP(384,[256,32,1],True)
   confidence.pt     ConfidenceGenerator.inference_without_update / update (latest_measurement)
+  tmp_state_dict.pt the weight hand-off file as wvn_learning_node.py:381-394 writes it (reference SimpleMLP + ConfidenceGenerator)
   segments.npz      reference SegmentExtractor on a synthetic map + the reference's shipped
                     known-answer assets/graph/{seg,center}.pt and graph.pt edge_index
   dino_wrapper.pt   reference DinoInterface.inference (its real transform / upsample code) wrapped
@@ -93,6 +94,19 @@ def make_mlp_init(ns):
          "first8": {k: v.flatten()[:8].clone() for k, v in sd.items()}},
         os.path.join(HERE, "mlp_init_384.pt"),
     )
+
+
+def make_handoff(ns):
+    """.tmp_state_dict.pt exactly as the reference's learning node writes it (wvn_learning_node.py:381-394),
+    from the reference's own SimpleMLP / ConfidenceGenerator (small dims)."""
+    torch.manual_seed(7)
+    model = ns.SimpleMLP(16, [8, 4, 1], True)
+    cg = ns.ConfidenceGenerator(std_factor=0.5, method="latest_measurement")
+    with torch.no_grad():
+        cg.mean[0], cg.std[0], cg.var[0, 0] = 0.37, 0.21, 0.0441
+    new_model_state_dict = model.state_dict()
+    new_model_state_dict["confidence_generator"] = cg.get_dict()
+    torch.save(new_model_state_dict, os.path.join(HERE, "tmp_state_dict.pt"))
 
 
 def make_confidence(ns):
@@ -223,6 +237,7 @@ if __name__ == "__main__":
     make_mlp_train(ns)
     make_mlp_init(ns)
     make_confidence(ns)
+    make_handoff(ns)
     make_segments(ns)
     make_dino_wrapper()
     for f in sorted(os.listdir(HERE)):

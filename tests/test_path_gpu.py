@@ -83,6 +83,28 @@ def test_dino_interface_dense_with_resize():
     assert rel_l2(got, ref) <= 2e-2
 
 
+def test_uint8_hwc_ingest_matches_float_path_and_oracle():
+    """camera frames (B,H,W,3) uint8 straight into the patch loader == ros_image_to_torch
+    (ToTensor / 255) + resize_image (NEAREST + center crop) + the float interface — bit-identical tokens — and
+    within the ViT tolerance of the oracle run on the reference's own chain of steps."""
+    from oracle.dino_vit import ViTConfig, synthetic_state_dict, vit_tokens
+    from oracle.wvn_path import ros_image_to_float, resize_image, wvn_transform
+    from wild_visual_navigation_b200.feature_extractor import DinoInterface
+
+    cfg = ViTConfig.from_name("vit_small", 8, 224)
+    sd = synthetic_state_dict(cfg, seed=4)
+    di = DinoInterface("cuda", input_size=224, backbone_type="vit_small", patch_size=8, state_dict=sd, max_batch=3, chunk=2)
+    u8 = torch.randint(0, 256, (3, 300, 404, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(6)).cuda()
+    tok_u8 = di.inference_tokens(u8)
+    img = ros_image_to_float(u8)                       # what the node hands to the feature extractor ...
+    tok_f = di.inference_tokens(img)
+    assert torch.equal(tok_u8, tok_f)
+    small = resize_image(img, 224)                     # ... after ImageProjector.resize_image
+    assert torch.equal(di.inference_tokens(small), tok_u8)
+    ref = vit_tokens(wvn_transform(small, 224), _to(sd, "cuda"), cfg)
+    assert rel_l2(tok_u8, ref) <= 2e-2
+
+
 def test_golden_dino_wrapper_oracle_matches_reference(golden_dir):
     """The oracle's wrapper semantics == the reference's own DinoInterface.inference code (golden)."""
     from oracle.dino_vit import ViTConfig, synthetic_state_dict

@@ -318,8 +318,24 @@ static int vit_check_loaded(wvn_vit* h, bool need_head) {
 
 constexpr int kDefaultSubAttn = 1 << 30;  // frames per (LN1, QKV, attention) pass; tuned on B200
 
+namespace {
+int vit_forward_impl(wvn_vit_t* h, const void* img, bool u8_hwc, int batch, int in_h, int in_w, int resized_h, int resized_w,
+                     float* tokens_out, void* stream);
+}
+
 int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_w, int resized_h, int resized_w,
                     float* tokens_out, void* stream) {
+  return vit_forward_impl(h, img, false, batch, in_h, in_w, resized_h, resized_w, tokens_out, stream);
+}
+
+int wvn_vit_forward_u8(wvn_vit_t* h, const unsigned char* img_hwc, int batch, int in_h, int in_w, int resized_h,
+                       int resized_w, float* tokens_out, void* stream) {
+  return vit_forward_impl(h, img_hwc, true, batch, in_h, in_w, resized_h, resized_w, tokens_out, stream);
+}
+
+namespace {
+int vit_forward_impl(wvn_vit_t* h, const void* img, bool u8_hwc, int batch, int in_h, int in_w, int resized_h, int resized_w,
+                     float* tokens_out, void* stream) {
   WVN_REQUIRE(h && img, "wvn_vit_forward: null argument");
   WVN_REQUIRE(batch > 0 && batch <= h->cfg.max_batch, "wvn_vit_forward: batch %d outside (0, %d]", batch, h->cfg.max_batch);
   WVN_REQUIRE(resized_h >= h->cfg.image_size && resized_w >= h->cfg.image_size,
@@ -342,7 +358,8 @@ int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_
     const int rows = nb * h->npad;
     float* x = reinterpret_cast<float*>(h->x.p);
     ia.batch = nb;
-    WVN_PROPAGATE(image_to_patches(img + static_cast<long long>(b0) * 3 * in_h * in_w, h->ape.p, ia, s));
+    const long long frame_bytes = static_cast<long long>(3) * in_h * in_w * (u8_hwc ? 1 : 4);
+    WVN_PROPAGATE(image_to_patches(static_cast<const char*>(img) + b0 * frame_bytes, u8_hwc, h->ape.p, ia, s));
     WVN_PROPAGATE(init_token_rows(x, h->wp<float>("cls_token"), h->wp<float>("pos_embed"), nb, h->npad, h->n_valid, D, s));
     {
       GemmArgs g;
@@ -447,6 +464,7 @@ int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_
   h->last_batch = batch;
   return WVN_OK;
 }
+}  // namespace
 
 int wvn_vit_stego_head(wvn_vit_t* h, int batch, float* out, void* stream) {
   WVN_REQUIRE(h && out, "wvn_vit_stego_head: null argument");

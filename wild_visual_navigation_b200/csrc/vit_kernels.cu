@@ -2,7 +2,11 @@
 //
 //   image_to_patches   : NEAREST resize + center crop + ImageNet normalisation + im2col -> bf16
 //                        (reference: dino_interface.py:52-59,81 transform, then the DINO
-//                         PatchEmbed Conv2d(3, D, p, p) expressed as a GEMM — SURVEY.md K1)
+//                         PatchEmbed Conv2d(3, D, p, p) expressed as a GEMM — SURVEY.md K1).
+//                        Source is either the float CHW tensor the reference hands to the interface or
+//                         the camera's uint8 HWC frame itself: ToTensor's `/ 255`
+//                        (ros_converter.py:113-126) and ImageProjector.resize_image's NEAREST resize +
+//                        center crop (image_projector.py:55-59,199-200) happen inside the loader.
 //   init_token_rows    : CLS row (cls_token + pos_embed[0]) and zeroed padding rows
 //   layernorm_rows     : LayerNorm(D, eps) over the fp32 residual stream -> bf16 GEMM operand
 //                        (optionally also the fp32 patch-token output, CLS dropped — K2/K7)
@@ -16,8 +20,11 @@ namespace {
 
 // One thread produces 8 consecutive K-elements (one patch row of one channel for p=8):
 // reads 8 floats that are contiguous in the source row when no resize happens.
-__global__ void image_to_patches_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out,
+template <bool U8_HWC>
+__global__ void image_to_patches_kernel(const void* __restrict__ img_raw, __nv_bfloat16* __restrict__ out,
                                         ImagePatchArgs a) {
+  const float* img = reinterpret_cast<const float*>(img_raw);
+  const unsigned char* img8 = reinterpret_cast<const unsigned char*>(img_raw);
   const int ps = a.patch;
   const int k_total = 3 * ps * ps;
   const int groups_per_row = k_total / 8;
@@ -39,12 +46,15 @@ __global__ void image_to_patches_kernel(const float* __restrict__ img, __nv_bflo
     const int sy = min(static_cast<int>(floorf((y + a.crop_top) * a.scale_y)), a.in_h - 1);
     const float mean = a.mean[c], inv_std = a.inv_std[c];
     const float* src_row = img + ((static_cast<long long>(b) * 3 + c) * a.in_h + sy) * a.in_w;
+    const unsigned char* src_row8 = img8 + (static_cast<long long>(b) * a.in_h + sy) * a.in_w * 3 + c;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int x = pw * ps + kx0 + i;
       const int sx = min(static_cast<int>(floorf((x + a.crop_left) * a.scale_x)), a.in_w - 1);
-      v[i] = (__ldg(src_row + sx) - mean) * inv_std;
+      // uint8: the same IEEE division torchvision's ToTensor performs, so both sources give identical patches
+      const float px = U8_HWC ? static_cast<float>(__ldg(src_row8 + 3 * sx)) / 255.f : __ldg(src_row + sx);
+      v[i] = (px - mean) * inv_std;
     }
     st_global_v4(out + prow * k_total + k0, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                  pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
@@ -123,15 +133,19 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ gam
 
 }  // namespace
 
-int image_to_patches(const float* img, void* out_bf16, const ImagePatchArgs& a, cudaStream_t stream) {
+int image_to_patches(const void* img, bool u8_hwc, void* out_bf16, const ImagePatchArgs& a, cudaStream_t stream) {
   WVN_REQUIRE(a.patch == 8 || a.patch == 16, "image_to_patches: patch size %d unsupported", a.patch);
   const long long total = static_cast<long long>(a.batch) * a.grid_h * a.grid_w * (3 * a.patch * a.patch / 8);
   const int threads = 256;
   long long blocks = (total + threads - 1) / threads;
   const long long max_blocks = static_cast<long long>(sm_count()) * 16;
   if (blocks > max_blocks) blocks = max_blocks;
-  image_to_patches_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-      img, reinterpret_cast<__nv_bfloat16*>(out_bf16), a);
+  if (u8_hwc)
+    image_to_patches_kernel<true><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        img, reinterpret_cast<__nv_bfloat16*>(out_bf16), a);
+  else
+    image_to_patches_kernel<false><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        img, reinterpret_cast<__nv_bfloat16*>(out_bf16), a);
   WVN_CHECK_LAUNCH("image_to_patches_kernel");
   return WVN_OK;
 }

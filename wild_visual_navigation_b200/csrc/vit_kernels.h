@@ -25,7 +25,8 @@ struct LayerNormArgs {
   int reverse = 0;  // walk the rows last-to-first (start where the producer kernel finished: those rows are still in L2)
 };
 
-int image_to_patches(const float* img, void* out_bf16, const ImagePatchArgs& a, cudaStream_t stream);
+// img: [batch, 3, in_h, in_w] fp32 in [0,1], or (u8_hwc) [batch, in_h, in_w, 3] uint8 RGB
+int image_to_patches(const void* img, bool u8_hwc, void* out_bf16, const ImagePatchArgs& a, cudaStream_t stream);
 int init_token_rows(float* x, const float* cls, const float* pos, int batch, int npad, int n_valid, int dim,
                     cudaStream_t stream);
 int layernorm_rows(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,

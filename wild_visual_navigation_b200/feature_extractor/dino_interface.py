@@ -61,7 +61,12 @@ class DinoInterface:
 
     @torch.no_grad()
     def inference_tokens(self, img: torch.Tensor) -> torch.Tensor:
-        """(B,3,H,W) in [0,1] -> final-norm patch tokens (B, h*w, D) fp32 — the fused path's product."""
+        """(B,3,H,W) in [0,1] -> final-norm patch tokens (B, h*w, D) fp32 — the fused path's product.
+        Also accepts the camera frames as they arrive, (B,H,W,3) uint8 RGB: ``ros_image_to_torch``
+        (ros_converter.py:113-126) and ``ImageProjector.resize_image`` (image_projector.py:199-200) are then
+        folded into the patch loader (4x less host->device traffic, no fp32 image round trip)."""
+        if img.dtype == torch.uint8:
+            return self._model.forward(img.to(self._device))
         return self._model.forward(img.to(self._device, dtype=torch.float32))
 
     @torch.no_grad()

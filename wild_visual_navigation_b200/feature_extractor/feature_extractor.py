@@ -97,8 +97,12 @@ class FeatureExtractor:
     def extract_batch(self, img, **kwargs):
         """Batched form of ``extract`` (no per-frame host sync): returns padded device tensors
         seg [B,H,W] i64, feat [B,smax,D], centers [B,smax,2], edges [B,E,2], n_edges [B], n_segments [B]."""
-        img = img.to(self._device, dtype=torch.float32)
-        B, _, H, W = img.shape
+        if img.dtype == torch.uint8:  # camera frames (B,H0,W0,3): ingest fused into the patch loader (§8f rank 1)
+            img = img.to(self._device)
+            B, H, W = img.shape[0], self._input_size, self._input_size
+        else:
+            img = img.to(self._device, dtype=torch.float32)
+            B, _, H, W = img.shape
         g = self._dino.grid
         # 1. segmentation (+ the one backbone pass)
         tokens = None

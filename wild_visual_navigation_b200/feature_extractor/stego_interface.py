@@ -59,9 +59,16 @@ class StegoInterface:
 
     @torch.no_grad()
     def inference(self, img: torch.Tensor):
-        """img (B,3,H,W) -> (linear_pred, cluster_pred), each (1,B,H,H) int32 like the reference."""
-        img = img.to(self._device, dtype=torch.float32)
-        B, _, H, W = img.shape
+        """img (B,3,H,W) -> (linear_pred, cluster_pred), each (1,B,H,H) int32 like the reference.
+        Camera frames (B,H0,W0,3) uint8 are accepted too: they are resized (NEAREST) / center-cropped to
+        ``input_size`` inside the patch loader, i.e. H = W = input_size as after ``ImageProjector.resize_image``."""
+        if img.dtype == torch.uint8:
+            img = img.to(self._device)
+            B, H, W = img.shape[0], self._cfg.input_size, self._cfg.input_size
+            assert not self._flip_tta, "flip TTA needs the float image (flip is applied to the transformed image)"
+        else:
+            img = img.to(self._device, dtype=torch.float32)
+            B, _, H, W = img.shape
         vit = self._dino._model
         g, npad = vit.grid, vit.npad
         if self._flip_tta:

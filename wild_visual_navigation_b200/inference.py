@@ -33,6 +33,16 @@ class TraversabilityInference:
         wvn_feature_extractor_node.py:407-450, runs at <= 1 Hz)."""
         self._mlp.set_params(self._model.flat_params)
 
+    def load_model(self, path: str) -> bool:
+        """The node's ``load_model`` (wvn_feature_extractor_node.py:407-446): pick up ``.tmp_state_dict.pt`` if the
+        learner wrote new weights; returns True when the MLP / confidence generator were updated."""
+        from .utils.handoff import read_tmp_state_dict
+
+        changed = read_tmp_state_dict(self._model, self._cg, path)
+        if changed:
+            self.refresh_weights()
+        return changed
+
     @torch.no_grad()
     def predict(self, img: torch.Tensor):
         """img (B,3,H,W) in [0,1] -> (trav (B,H,H), conf (B,H,H)) fp32 on the device."""

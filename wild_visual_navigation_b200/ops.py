@@ -161,14 +161,21 @@ class ViTBackbone:
         self._set("norm.bias", sd["norm.bias"])
 
     def forward(self, img: torch.Tensor, resized_hw=None) -> torch.Tensor:
-        """img: (B,3,H,W) f32 CUDA in [0,1] -> final-norm patch tokens (B, P, D) f32."""
-        B, C, H, W = img.shape
-        assert C == 3 and img.dtype == torch.float32
+        """img: (B,3,H,W) f32 CUDA in [0,1], or the camera frames themselves (B,H,W,3) uint8 RGB
+        -> final-norm patch tokens (B, P, D) f32."""
         img = img.contiguous()
+        if img.dtype == torch.uint8:
+            B, H, W, C = img.shape
+            fn = lib().wvn_vit_forward_u8
+        else:
+            B, C, H, W = img.shape
+            assert img.dtype == torch.float32
+            fn = lib().wvn_vit_forward
+        assert C == 3
         if resized_hw is None:
             resized_hw = _resized_size(H, W, self.image_size)
         tokens = torch.empty(B, self.P, self.dim, device=img.device, dtype=torch.float32)
-        check(lib().wvn_vit_forward(self._h, ptr(img), B, H, W, resized_hw[0], resized_hw[1], ptr(tokens), stream()))
+        check(fn(self._h, ptr(img), B, H, W, resized_hw[0], resized_hw[1], ptr(tokens), stream()))
         return tokens
 
     def stego_head(self, batch: int) -> torch.Tensor:

@@ -196,6 +196,13 @@ class TraversabilityEstimator:
                 tr.step_counter.fill_(int(st["step"]))
             off += n
 
+    def write_model_handoff(self, path: str) -> str:
+        """The learner's side of the weight hand-off (wvn_learning_node.py:381-394): ``.tmp_state_dict.pt``."""
+        from ..utils.handoff import write_tmp_state_dict
+
+        with self._learning_lock:
+            return write_tmp_state_dict(self._model, self._traversability_loss._confidence_generator, path)
+
     def save_checkpoint(self, mission_path: str, checkpoint_name: str = "last_checkpoint.pt"):
         with self._learning_lock:
             self._pause_training = True
