@@ -167,6 +167,15 @@ int wvn_segment_reduce(const long long* seg, int batch, int h, int w, int smax, 
 int wvn_segment_relabel(long long* seg, int batch, long long pix_per_frame, int num_labels, int* scratch, int* counts,
                         void* stream);
 
+/* Supervision label pooling — replaces MissionNode.update_supervision_signal (traversability_estimator/nodes.py:400-440):
+ *   signal = supervision_mask.nanmean(0);  per segment s: mean of signal over the segment's non-NaN pixels,
+ *   nan_to_num(0);  valid = signal_mean > 0
+ * without the reference's (H, W, S) one-hot expansion.  seg: [batch, h, w] int64 (ids outside [0, smax) ignored);
+ * mask: [batch, channels, h, w] fp32 with NaN = unlabelled; y: [batch, smax] fp32; y_valid: [batch, smax] uint8;
+ * count_ws: [batch, smax] fp32 scratch. */
+int wvn_supervision_pool(const long long* seg, const float* mask, int batch, int channels, int h, int w, int smax,
+                         float* y, unsigned char* y_valid, float* count_ws, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Traversability MLP inference over every pixel — replaces
  *   x = dense_feat[0].permute(1,2,0).reshape(-1, D); prediction = model.forward(Data(x));

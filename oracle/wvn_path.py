@@ -74,6 +74,25 @@ def dino_inference(img: torch.Tensor, sd: dict, cfg: ViTConfig) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------
+# Supervision label pooling                  (traversability_estimator/nodes.py:400-440)
+# ------------------------------------------------------------------------------------------
+@torch.no_grad()
+def update_supervision_signal(supervision_mask: torch.Tensor, feature_segments: torch.Tensor):
+    """``MissionNode.update_supervision_signal``: mask (C,H,W) with NaN = unlabelled, segments (H,W) long ->
+    (supervision_signal (S,), supervision_signal_valid (S,)), S = segments.max() + 1.  Same arithmetic as the
+    reference (nanmean over channels, per-segment sum / count of the non-NaN pixels, nan_to_num(0), > 0) without
+    its (H, W, S) expansion."""
+    signal = supervision_mask.nanmean(axis=0)
+    S = int(feature_segments.max()) + 1
+    ok = ~torch.isnan(signal)
+    ids = feature_segments[ok]
+    cnt = torch.zeros(S, dtype=signal.dtype, device=signal.device).index_add_(0, ids, torch.ones_like(signal[ok]))
+    tot = torch.zeros(S, dtype=signal.dtype, device=signal.device).index_add_(0, ids, signal[ok])
+    mean = (tot / cnt).nan_to_num(0)
+    return mean, mean > 0
+
+
+# ------------------------------------------------------------------------------------------
 # SegmentExtractor                              (feature_extractor/segment_extractor.py:40-92)
 # ------------------------------------------------------------------------------------------
 @torch.no_grad()

@@ -11,6 +11,7 @@ Fixtures
   mlp_train.pt      reference SimpleMLP + TraversabilityLoss + torch.optim.Adam, 3 steps (small dims)
   mlp_init_384.pt   checksum of the seed-42 init of the real-size SimpleMLP(384,[256,32,1],True)
   confidence.pt     ConfidenceGenerator.inference_without_update / update (latest_measurement)
+  supervision.pt    MissionNode.update_supervision_signal (the reference's method source, executed from the reference file)
   tmp_state_dict.pt the weight hand-off file as wvn_learning_node.py:381-394 writes it (reference SimpleMLP + ConfidenceGenerator)
   segments.npz      reference SegmentExtractor on a synthetic map + the reference's shipped
                     known-answer assets/graph/{seg,center}.pt and graph.pt edge_index
@@ -107,6 +108,32 @@ def make_handoff(ns):
     new_model_state_dict = model.state_dict()
     new_model_state_dict["confidence_generator"] = cg.get_dict()
     torch.save(new_model_state_dict, os.path.join(HERE, "tmp_state_dict.pt"))
+
+
+def make_supervision():
+    """Runs the reference's OWN ``MissionNode.update_supervision_signal`` (nodes.py:400-440).  nodes.py cannot be
+    imported here (liegroups / kornia / networkx are absent), so the method's source is taken from the reference
+    file with ``ast`` and executed against a bare namespace object — nothing is copied into this repository."""
+    import ast
+
+    path = os.path.join(ref_import.REF_ROOT, "wild_visual_navigation/traversability_estimator/nodes.py")
+    src = open(path).read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "update_supervision_signal")
+    import textwrap
+
+    code = "import torch\n" + textwrap.dedent("\n".join(src.splitlines()[fn.lineno - 1 : fn.end_lineno]))
+    scope = {}
+    exec(compile(code, path, "exec"), scope)
+    g = torch.Generator().manual_seed(13)
+    seg = synthetic_segments(48, 48, 9, seed=6).long()
+    mask = torch.rand(3, 48, 48, generator=g)
+    mask[torch.rand(3, 48, 48, generator=g) < 0.55] = float("nan")
+    mask[:, seg == 4] = float("nan")       # one segment without any label
+    mask[1:, seg == 2] = float("nan")      # one segment labelled in a single channel only
+    node = types.SimpleNamespace(_supervision_mask=mask.clone(), _features=torch.zeros(9, 4), _feature_segments=seg.clone())
+    scope["update_supervision_signal"](node)
+    torch.save({"seg": seg, "mask": mask, "signal": node._supervision_signal, "valid": node._supervision_signal_valid},
+               os.path.join(HERE, "supervision.pt"))
 
 
 def make_confidence(ns):
@@ -238,6 +265,7 @@ if __name__ == "__main__":
     make_mlp_init(ns)
     make_confidence(ns)
     make_handoff(ns)
+    make_supervision()
     make_segments(ns)
     make_dino_wrapper()
     for f in sorted(os.listdir(HERE)):

@@ -220,6 +220,32 @@ def test_pixel_inference_vs_oracle(vit448, mode, monkeypatch):
         assert 0.02 < c_ref.float().mean() < 0.98  # the test is not saturated
 
 
+def test_supervision_label_pooling_vs_reference_golden(golden_dir):
+    """the pooled labels of the CUDA reduction == MissionNode.update_supervision_signal
+    (the reference's own method, executed by make_golden.py), batched and with ids outside [0, smax) ignored."""
+    from wild_visual_navigation_b200 import ops
+
+    g = torch.load(os.path.join(golden_dir, "supervision.pt"))
+    seg, mask = g["seg"].cuda(), g["mask"].cuda()
+    S = int(seg.max()) + 1
+    seg2 = seg.clone()
+    seg2[:3] = -1                                   # frame 1: a few ignored pixels (random-pixel mode marks them -1)
+    y, valid = ops.pool_supervision(torch.stack([seg, seg2]), torch.stack([mask, mask]), S + 3)
+    assert (y[0, :S].cpu() - g["signal"]).abs().max() < 1e-6
+    assert torch.equal(valid[0, :S].cpu(), g["valid"])
+    assert (y[:, S:] == 0).all() and not valid[:, S:].any()
+    from oracle.wvn_path import update_supervision_signal
+    keep = seg2 >= 0
+    m2 = mask.clone()
+    m2[:, ~keep] = float("nan")
+    ref2, v2 = update_supervision_signal(m2.cpu(), seg.cpu())
+    assert (y[1, :S].cpu() - ref2).abs().max() < 1e-6 and torch.equal(valid[1, :S].cpu(), v2)
+    # single-channel (H, W) mask form
+    y1, _ = ops.pool_supervision(seg[None], mask[0][None], S)
+    ref1, _ = update_supervision_signal(mask[:1].cpu(), seg.cpu())
+    assert (y1[0].cpu() - ref1).abs().max() < 1e-6
+
+
 def test_train_step_vs_reference_golden(golden_dir):
     """3 Adam steps on the reference-generated fixture (reference SimpleMLP + TraversabilityLoss + Adam)."""
     from wild_visual_navigation_b200 import ops

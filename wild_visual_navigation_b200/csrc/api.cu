@@ -549,6 +549,12 @@ int wvn_segment_relabel(long long* seg, int batch, long long pix_per_frame, int 
   return relabel_compact(seg, scratch, counts, batch, pix_per_frame, num_labels, S(stream));
 }
 
+int wvn_supervision_pool(const long long* seg, const float* mask, int batch, int channels, int h, int w, int smax,
+                         float* y, unsigned char* y_valid, float* count_ws, void* stream) {
+  WVN_REQUIRE(seg && mask && y && y_valid && count_ws, "wvn_supervision_pool: null argument");
+  return supervision_pool(seg, mask, batch, channels, h, w, smax, y, y_valid, count_ws, S(stream));
+}
+
 }  // extern "C"
 
 // ============================================================================================

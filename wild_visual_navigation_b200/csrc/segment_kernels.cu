@@ -295,6 +295,53 @@ label_apply_kernel(long long* __restrict__ seg, const int* __restrict__ remap, i
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Supervision label pooling (MissionNode.update_supervision_signal, nodes.py:400-440): the reference expands
+// the (H, W) signal against an (H, W, S) one-hot of the segment map (20-200 MB) to average it per segment;
+// here each block privatises (sum, count) per segment in shared memory and flushes with two atomics per
+// touched segment.  signal = nanmean over the mask's channels; NaN (no channel labelled) pixels are skipped.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+supervision_pool_kernel(const long long* __restrict__ seg, const float* __restrict__ mask, int channels,
+                        long long pix, int smax, float* __restrict__ sum, float* __restrict__ cnt) {
+  extern __shared__ float sh[];  // [smax] sums | [smax] counts
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * smax; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const long long* sg = seg + b * pix;
+  const float* mk = mask + static_cast<long long>(b) * channels * pix;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < pix;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float s = 0.f;
+    int n = 0;
+    for (int c = 0; c < channels; ++c) {
+      const float v = __ldg(mk + c * pix + p);
+      if (v == v) { s += v; ++n; }
+    }
+    const long long id = sg[p];
+    if (n > 0 && id >= 0 && id < smax) {
+      atomicAdd(&sh[id], s / static_cast<float>(n));
+      atomicAdd(&sh[smax + id], 1.f);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < smax; i += blockDim.x) {
+    if (sh[smax + i] > 0.f) {
+      atomicAdd(&sum[b * smax + i], sh[i]);
+      atomicAdd(&cnt[b * smax + i], sh[smax + i]);
+    }
+  }
+}
+
+__global__ void supervision_finalize_kernel(float* __restrict__ y, const float* __restrict__ cnt,
+                                            unsigned char* __restrict__ valid, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = cnt[i] > 0.f ? y[i] / cnt[i] : 0.f;  // 0 / 0 -> nan -> nan_to_num(0) in the reference
+  y[i] = v;
+  valid[i] = v > 0.f ? 1 : 0;
+}
+
 }  // namespace
 
 int segment_accumulate(const long long* seg, const SegmentArgs& a, unsigned long long* stats, float* wseg,
@@ -374,6 +421,23 @@ int relabel_compact(long long* seg, int* scratch, int* counts, int batch, long l
   WVN_CHECK_LAUNCH("label_scan_kernel");
   label_apply_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(seg, scratch, batch, pix_per_frame, num_labels);
   WVN_CHECK_LAUNCH("label_apply_kernel");
+  return WVN_OK;
+}
+
+int supervision_pool(const long long* seg, const float* mask, int batch, int channels, int h, int w, int smax, float* y,
+                     unsigned char* y_valid, float* cnt_ws, cudaStream_t stream) {
+  WVN_REQUIRE(batch > 0 && channels > 0 && h > 0 && w > 0 && smax > 0 && smax <= 4096,
+              "supervision_pool: bad geometry (batch=%d channels=%d %dx%d smax=%d)", batch, channels, h, w, smax);
+  const long long pix = static_cast<long long>(h) * w;
+  WVN_CHECK_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * batch * smax, stream));
+  WVN_CHECK_CUDA(cudaMemsetAsync(cnt_ws, 0, sizeof(float) * batch * smax, stream));
+  const int per_frame = static_cast<int>(std::min<long long>((pix + 256 * 16 - 1) / (256 * 16), 64));
+  supervision_pool_kernel<<<dim3(per_frame, batch), 256, 2 * smax * sizeof(float), stream>>>(seg, mask, channels, pix, smax,
+                                                                                            y, cnt_ws);
+  WVN_CHECK_LAUNCH("supervision_pool_kernel");
+  const int n = batch * smax;
+  supervision_finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(y, cnt_ws, y_valid, n);
+  WVN_CHECK_LAUNCH("supervision_finalize_kernel");
   return WVN_OK;
 }
 

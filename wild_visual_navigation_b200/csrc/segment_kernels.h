@@ -29,4 +29,9 @@ int adjacency_emit(const unsigned int* adj, long long* edges, int* n_edges, int 
 int relabel_compact(long long* seg, int* scratch, int* counts, int batch, long long pix_per_frame, int num_labels,
                     cudaStream_t stream);
 
+// Per-segment mean of a supervision mask (NaN = unlabelled), nodes.py:400-440.  mask: [B, C, h, w] f32;
+// y: [B, smax] f32 (0 where no labelled pixel), y_valid: [B, smax] u8 (y > 0); cnt_ws: [B, smax] f32 scratch.
+int supervision_pool(const long long* seg, const float* mask, int batch, int channels, int h, int w, int smax, float* y,
+                     unsigned char* y_valid, float* cnt_ws, cudaStream_t stream);
+
 }  // namespace wvn

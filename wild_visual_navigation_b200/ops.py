@@ -95,6 +95,22 @@ def segment_reduce(seg, smax, tokens=None, grid=None, want_centers=True, want_ed
     return {"feat": feat, "centers": centers, "edges": edges, "n_edges": n_edges, "max_edges": max_edges}
 
 
+def pool_supervision(seg: torch.Tensor, mask: torch.Tensor, smax: int):
+    """Per-segment supervision labels (MissionNode.update_supervision_signal, nodes.py:400-440).
+    seg (B,H,W) int64; mask (B,C,H,W) or (B,H,W) fp32 with NaN = unlabelled -> y (B,smax) f32, y_valid (B,smax) bool."""
+    _C.require_device()
+    if mask.dim() == 3:
+        mask = mask[:, None]
+    B, C, H, W = mask.shape
+    assert seg.shape == (B, H, W) and seg.dtype == torch.int64 and mask.dtype == torch.float32
+    seg, mask = seg.contiguous(), mask.contiguous()
+    y = torch.empty(B, smax, device=seg.device, dtype=torch.float32)
+    valid = torch.empty(B, smax, device=seg.device, dtype=torch.uint8)
+    ws = torch.empty(B, smax, device=seg.device, dtype=torch.float32)
+    check(lib().wvn_supervision_pool(ptr(seg), ptr(mask), B, C, H, W, smax, ptr(y), ptr(valid), ptr(ws), stream()))
+    return y, valid.bool()
+
+
 def relabel(seg, num_labels):
     """In-place relabel of each frame of seg [B,H,W] to 0..S-1; returns counts [B] int32."""
     B = seg.shape[0]

@@ -53,6 +53,17 @@ class MissionNode:
     def is_valid(self):
         return self.features is not None and self.supervision_signal is not None
 
+    def update_supervision_signal(self, supervision_mask: torch.Tensor, feature_segments: torch.Tensor):
+        """Per-segment labels from a rendered supervision mask (nodes.py:400-440): ``supervision_mask`` (C,H,W) or
+        (H,W) with NaN = unlabelled, ``feature_segments`` (H,W) long.  One CUDA reduction instead of the reference's
+        (H, W, S) expansion; S = number of feature rows."""
+        from .. import ops
+
+        mask = supervision_mask if supervision_mask.dim() == 3 else supervision_mask[None]
+        y, valid = ops.pool_supervision(feature_segments[None].contiguous(), mask[None].float().contiguous(),
+                                        int(self.features.shape[0]))
+        self.supervision_signal, self.supervision_signal_valid = y[0], valid[0]
+
     def as_pyg_data(self, anomaly_detection: bool = False):
         return Data(x=self.features, y=self.supervision_signal, y_valid=self.supervision_signal_valid)
 
