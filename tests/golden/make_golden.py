@@ -12,6 +12,8 @@ Fixtures
   mlp_init_384.pt   checksum of the seed-42 init of the real-size SimpleMLP(384,[256,32,1],True)
   confidence.pt     ConfidenceGenerator.inference_without_update / update (latest_measurement)
   supervision.pt    MissionNode.update_supervision_signal (the reference's method source, executed from the reference file)
+  sparsify.pt       FeatureExtractor.sparsify_features (loop + cumsum variants) and segment_stego's relabel loop,
+                    the reference's method sources executed from the reference file
   tmp_state_dict.pt the weight hand-off file as wvn_learning_node.py:381-394 writes it (reference SimpleMLP + ConfidenceGenerator)
   segments.npz      reference SegmentExtractor on a synthetic map + the reference's shipped
                     known-answer assets/graph/{seg,center}.pt and graph.pt edge_index
@@ -134,6 +136,42 @@ def make_supervision():
     scope["update_supervision_signal"](node)
     torch.save({"seg": seg, "mask": mask, "signal": node._supervision_signal, "valid": node._supervision_signal_valid},
                os.path.join(HERE, "supervision.pt"))
+
+
+def _reference_method(rel_path, name):
+    """A method of a reference class whose module cannot be imported here: its source is read from the reference file
+    with ``ast`` and compiled as a free function (nothing is copied into this repository)."""
+    import ast
+    import textwrap
+
+    path = os.path.join(ref_import.REF_ROOT, rel_path)
+    src = open(path).read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == name)
+    code = "import torch\n" + textwrap.dedent("\n".join(src.splitlines()[fn.lineno - 1 : fn.end_lineno]))
+    scope = {}
+    exec(compile(code, path, "exec"), scope)
+    return scope[name]
+
+
+def make_sparsify():
+    """The reference's OWN ``FeatureExtractor.sparsify_features`` (default loop and cumsum variant,
+    feature_extractor.py:310-398) and the relabel loop of ``segment_stego`` (:237-249)."""
+    fe = "wild_visual_navigation/feature_extractor/feature_extractor.py"
+    sparsify, segment_stego = _reference_method(fe, "sparsify_features"), _reference_method(fe, "segment_stego")
+    g = torch.Generator().manual_seed(17)
+    seg = synthetic_segments(24, 24, 5, seed=8).long()
+    dense = torch.randn(1, 6, 24, 24, generator=g)
+    me = types.SimpleNamespace(_feature_type="dino", _segmentation_type="stego")
+    feat = sparsify(me, dense, seg)
+    feat_cumsum = sparsify(me, dense.clone(), seg.clone(), cumsum_trick=True)
+    # cluster ids as the STEGO probe emits them (arbitrary subset of 0..26), relabelled to 0..S-1
+    labels = torch.tensor([3, 7, 19, 20, 26])
+    raw = labels[seg][None, None]
+    extractor = types.SimpleNamespace(inference=lambda img: None, cluster_segments=raw.clone())
+    me2 = types.SimpleNamespace(_extractor=extractor, _device="cpu")
+    relabelled = segment_stego(me2, torch.zeros(1, 3, 24, 24))
+    torch.save({"dense": dense, "seg": seg, "feat": feat, "feat_cumsum": feat_cumsum, "raw_clusters": raw,
+                "relabelled": relabelled}, os.path.join(HERE, "sparsify.pt"))
 
 
 def make_confidence(ns):
@@ -266,6 +304,7 @@ if __name__ == "__main__":
     make_confidence(ns)
     make_handoff(ns)
     make_supervision()
+    make_sparsify()
     make_segments(ns)
     make_dino_wrapper()
     for f in sorted(os.listdir(HERE)):

@@ -220,6 +220,23 @@ def test_pixel_inference_vs_oracle(vit448, mode, monkeypatch):
         assert 0.02 < c_ref.float().mean() < 0.98  # the test is not saturated
 
 
+def test_relabel_and_pooling_vs_reference_golden(golden_dir):
+    """CUDA relabel + segment pooling against the outputs of the reference's own segment_stego relabel loop and
+    sparsify_features (sparsify.pt).  Pooling is fed tokens at full resolution (grid == image), so the fused
+    weights-by-linearity path must reproduce the per-pixel means exactly (1e-5)."""
+    from wild_visual_navigation_b200 import ops
+
+    g = torch.load(os.path.join(golden_dir, "sparsify.pt"))
+    raw = g["raw_clusters"][0].cuda().long().contiguous()         # (1, H, W) arbitrary cluster ids
+    counts = ops.relabel(raw, 27)
+    assert int(counts[0]) == 5 and torch.equal(raw.cpu(), g["relabelled"][0])
+    dense = g["dense"].cuda()                                       # (1, D, H, W): use it as a token grid of the same size
+    _, D, H, W = dense.shape
+    tokens = dense[0].permute(1, 2, 0).reshape(1, H * W, D).contiguous()
+    r = ops.segment_reduce(raw, 8, tokens=tokens, grid=(H, W), want_centers=False, want_edges=False)
+    assert (r["feat"][0, :5].cpu() - g["feat"]).abs().max() < 1e-5
+
+
 def test_supervision_label_pooling_vs_reference_golden(golden_dir):
     """the pooled labels of the CUDA reduction == MissionNode.update_supervision_signal
     (the reference's own method, executed by make_golden.py), batched and with ids outside [0, smax) ignored."""
