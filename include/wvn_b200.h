@@ -119,7 +119,14 @@ int wvn_vit_set_weight(wvn_vit_t* h, const char* name, const float* data, long l
 int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_w, int resized_h, int resized_w,
                     float* tokens_out, void* stream);
 
-/* Same, from the camera frame itself: img_hwc [batch, in_h, in_w, 3] uint8 RGB.  Folds into the patch loader the
+/* Flip test-time augmentation of STEGO ([EXTERNAL] Stego.get_code, called at stego_interface.py:91): the `batch`
+ * frames are run twice, the second time on the horizontal flip of the TRANSFORMED (resized + cropped + normalised)
+ * image; tokens_out [2*batch, P, dim] (second half = flipped pass) and the activation layout hold 2*batch frames,
+ * so 2*batch <= max_batch. */
+int wvn_vit_forward_tta(wvn_vit_t* h, const float* img, int batch, int in_h, int in_w, int resized_h, int resized_w,
+                        float* tokens_out, void* stream);
+
+/* Same as wvn_vit_forward, from the camera frame itself: img_hwc [batch, in_h, in_w, 3] uint8 RGB.  Folds into the patch loader the
  * two steps that precede the interface in the reference's node:
  *   ros_image_to_torch  — torchvision ToTensor: HWC uint8 -> CHW float / 255   (ros_converter.py:113-126)
  *   ImageProjector.resize_image — Resize(h, NEAREST) + CenterCrop(h)            (image_projector.py:55-59,199-200)

@@ -14,7 +14,10 @@ Restated from the public STEGO code [EXTERNAL-RECALLED, SURVEY.md §8 a4]:
 * ``StegoInterface.inference`` then upsamples code bilinear(align_corners=True) to (H, H) and the
   predictions 'nearest' to (H, H) as int.
 
-PARITY STATUS: "parity unpinned" — no upstream weights or golden outputs exist in the reference.
+PARITY STATUS: the head / probe arithmetic is "parity unpinned" (no upstream weights or golden outputs exist in
+the reference); the reference's own wrapper around it (transform, (H, H) interpolation rules, int cast, return order)
+IS pinned: tests/golden/stego_wrapper.pt is produced by running the reference's StegoInterface.inference around a shim
+model built from the functions below (make_golden.py).
 """
 from __future__ import annotations
 
@@ -68,13 +71,17 @@ def postprocess(code: torch.Tensor, out_hw: tuple[int, int], hd: dict):
 
 
 @torch.no_grad()
-def stego_inference(feats: torch.Tensor, feats_flipped: torch.Tensor | None, hd: dict, img_hw: tuple[int, int]):
+def stego_inference(feats: torch.Tensor, feats_flipped: torch.Tensor | None, hd: dict, img_hw: tuple[int, int],
+                    out_h: int | None = None):
     """feats: backbone map of the transformed image; feats_flipped: backbone map of its horizontal
-    flip (None disables the flip TTA).  Returns (code_up (B,dim,H,H), cluster (B,H,H), linear (B,H,H))."""
+    flip (None disables the flip TTA).  ``img_hw``: size of the TRANSFORMED image (what ``postprocess`` upsamples the
+    code to, stego_interface.py:91-100); ``out_h``: height H of the ORIGINAL image — the wrapper's final outputs are
+    (H, H) (stego_interface.py:104-109); defaults to img_hw[0] (no resize in the transform).
+    Returns (code_up (B,dim,H,H), cluster (B,H,H), linear (B,H,H))."""
     code = head_code(feats, hd)
     if feats_flipped is not None:
         code = (code + head_code(feats_flipped, hd).flip(dims=[3])) / 2
-    H = img_hw[0]
+    H = img_hw[0] if out_h is None else out_h
     cluster, linear = postprocess(code, img_hw, hd)
     code_up = F.interpolate(code, (H, H), mode="bilinear", align_corners=True)
     cluster = F.interpolate(cluster[None].float(), (H, H), mode="nearest").int()[0]

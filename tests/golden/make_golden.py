@@ -17,6 +17,8 @@ Fixtures
   tmp_state_dict.pt the weight hand-off file as wvn_learning_node.py:381-394 writes it (reference SimpleMLP + ConfidenceGenerator)
   segments.npz      reference SegmentExtractor on a synthetic map + the reference's shipped
                     known-answer assets/graph/{seg,center}.pt and graph.pt edge_index
+  stego_wrapper.pt  reference StegoInterface.inference (its real transform / interpolation code) around a shim Stego
+                    model made of the oracle's restated head + backbone (tiny config)
   dino_wrapper.pt   reference DinoInterface.inference (its real transform / upsample code) wrapped
                     around the oracle's restated ViT (tiny config) via omegaconf/stego shims
 """
@@ -296,6 +298,57 @@ def make_dino_wrapper():
                os.path.join(HERE, "dino_wrapper.pt"))
 
 
+def make_stego_wrapper():
+    """The reference's own ``StegoInterface.inference`` (stego_interface.py:73-111: transform, code -> bilinear
+    align_corners=True to (H, H), predictions -> nearest (H, H) int, return order) around a shim ``Stego`` model whose
+    ``get_code`` / ``postprocess`` are the oracle's restated head on the oracle's restated backbone."""
+    from oracle import stego_head
+
+    cfg = ViTConfig(image_size=32, patch_size=8, dim=32, depth=2, heads=2, mlp_dim=64, pretrain_grid=2)
+    sd = synthetic_state_dict(cfg, seed=21, attn_std=0.3)
+    hd = stego_head.synthetic_head(32, code_dim=10, n_clusters=6, n_classes=5, seed=4)
+
+    class _Stego(torch.nn.Module):
+        def get_code(self, img):  # Stego.get_code: horizontal-flip TTA
+            code = stego_head.head_code(vit_feature_map(img, sd, cfg), hd)
+            code_f = stego_head.head_code(vit_feature_map(img.flip(dims=[3]), sd, cfg), hd)
+            return (code + code_f.flip(dims=[3])) / 2
+
+        def postprocess(self, code, img, use_crf_cluster, use_crf_linear, image_clustering):
+            assert not (use_crf_cluster or use_crf_linear or image_clustering)
+            return stego_head.postprocess(code, tuple(img.shape[-2:]), hd)
+
+        @classmethod
+        def load_from_checkpoint(cls, path, n_image_clusters=None):
+            return cls()
+
+    class _Cfg(dict):
+        def is_empty(self): return len(self) == 0
+        __getattr__ = dict.__getitem__
+
+    om = types.ModuleType("omegaconf")
+    om.OmegaConf = types.SimpleNamespace(create=lambda d: _Cfg(d))
+    pt = types.ModuleType("pytictac"); pt.Timer = object
+    st = types.ModuleType("stego"); st.STEGO_ROOT_DIR = "/nonexistent"
+    sts = types.ModuleType("stego.stego"); sts.Stego = _Stego
+    std = types.ModuleType("stego.data"); std.create_cityscapes_colormap = lambda: None
+    sys.modules.update({"omegaconf": om, "pytictac": pt, "stego": st, "stego.stego": sts, "stego.data": std})
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_stego_interface", os.path.join(ref_import.REF_ROOT, "wild_visual_navigation/feature_extractor/stego_interface.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    si = mod.StegoInterface(device="cpu", input_size=32, n_image_clusters=6, run_crf=False, run_clustering=False)
+    g = torch.Generator().manual_seed(10)
+    img = torch.rand(2, 3, 40, 52, generator=g)  # non-square: the transform resizes (NEAREST) and crops
+    linear, cluster = si.inference(img.clone())
+    torch.save({"vit_seed": 21, "attn_std": 0.3, "cfg": cfg.__dict__, "head_seed": 4, "head_dims": (32, 10, 6, 5),
+                "img": img, "linear": linear, "cluster": cluster, "features": si.features},
+               os.path.join(HERE, "stego_wrapper.pt"))
+    for k in ("omegaconf", "pytictac", "stego", "stego.stego", "stego.data"):
+        sys.modules.pop(k, None)
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "needs /root/reference"
     ns = ref_import.load()
@@ -307,5 +360,6 @@ if __name__ == "__main__":
     make_sparsify()
     make_segments(ns)
     make_dino_wrapper()
+    make_stego_wrapper()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -117,8 +117,8 @@ def test_golden_dino_wrapper_oracle_matches_reference(golden_dir):
     assert (dino_inference(g["img2"], sd, cfg) - g["out2"]).abs().max() < 1e-5
 
 
-@pytest.mark.parametrize("flip_tta", [False, True])
-def test_stego_head_and_segments(flip_tta):
+@pytest.mark.parametrize("flip_tta,hw", [(False, (224, 224)), (True, (224, 224)), (True, (270, 360))])
+def test_stego_head_and_segments(flip_tta, hw):
     from oracle.dino_vit import ViTConfig, synthetic_state_dict, vit_feature_map
     from oracle.stego_head import stego_inference, synthetic_head
     from oracle.wvn_path import wvn_transform
@@ -129,14 +129,15 @@ def test_stego_head_and_segments(flip_tta):
     hd = synthetic_head(384, 90, 32, 27, seed=3)
     si = StegoInterface("cuda", input_size=224, backbone_type="vit_small", patch_size=8, head_state_dict=hd,
                         backbone_state_dict=sd, flip_tta=flip_tta, max_batch=2)
-    img = torch.rand(2, 3, 224, 224, generator=torch.Generator().manual_seed(7)).cuda()
+    H, W = hw  # (270, 360): the transform resizes (NEAREST) + crops; outputs are (H, H) (stego_interface.py:104-109)
+    img = torch.rand(2, 3, H, W, generator=torch.Generator().manual_seed(7)).cuda()
     lin, clu = si.inference(img)
     sdc, hdc = _to(sd, "cuda"), _to(hd, "cuda")
     timg = wvn_transform(img, 224)
     feats = vit_feature_map(timg, sdc, cfg)
     feats_f = vit_feature_map(timg.flip(dims=[3]), sdc, cfg) if flip_tta else None
-    code_ref, clu_ref, lin_ref = stego_inference(feats, feats_f, hdc, (224, 224))
-    assert clu.shape == (1, 2, 224, 224) and clu.dtype == torch.int32
+    code_ref, clu_ref, lin_ref = stego_inference(feats, feats_f, hdc, (224, 224), out_h=H)
+    assert clu.shape == (1, 2, H, H) and clu.dtype == torch.int32
     agree_c = (clu[0] == clu_ref).float().mean().item()
     agree_l = (lin[0] == lin_ref).float().mean().item()
     code = si.features

@@ -53,6 +53,7 @@ SIGNATURES = {
     "wvn_vit_set_weight": (_I, [_P, c_char_p, _P, _L]),
     "wvn_vit_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "wvn_vit_forward_u8": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "wvn_vit_forward_tta": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "wvn_vit_stego_head": (_I, [_P, _I, _P, _P]),
     "wvn_vit_npad": (_I, [_P]),
     "wvn_upsample_dense": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),

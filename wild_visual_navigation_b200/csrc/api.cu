@@ -320,7 +320,12 @@ constexpr int kDefaultSubAttn = 1 << 30;  // frames per (LN1, QKV, attention) pa
 
 namespace {
 int vit_forward_impl(wvn_vit_t* h, const void* img, bool u8_hwc, int batch, int in_h, int in_w, int resized_h, int resized_w,
-                     float* tokens_out, void* stream);
+                     float* tokens_out, void* stream, bool flip_tta = false);
+}
+
+int wvn_vit_forward_tta(wvn_vit_t* h, const float* img, int batch, int in_h, int in_w, int resized_h, int resized_w,
+                        float* tokens_out, void* stream) {
+  return vit_forward_impl(h, img, false, batch, in_h, in_w, resized_h, resized_w, tokens_out, stream, true);
 }
 
 int wvn_vit_forward(wvn_vit_t* h, const float* img, int batch, int in_h, int in_w, int resized_h, int resized_w,
@@ -334,8 +339,11 @@ int wvn_vit_forward_u8(wvn_vit_t* h, const unsigned char* img_hwc, int batch, in
 }
 
 namespace {
-int vit_forward_impl(wvn_vit_t* h, const void* img, bool u8_hwc, int batch, int in_h, int in_w, int resized_h, int resized_w,
-                     float* tokens_out, void* stream) {
+// flip_tta: `batch` source frames are run twice — frames [batch, 2*batch) of the activation layout / tokens_out are
+// the backbone's output on the horizontally flipped TRANSFORMED images (Stego.get_code's second pass).
+int vit_forward_impl(wvn_vit_t* h, const void* img, bool u8_hwc, int src_batch, int in_h, int in_w, int resized_h, int resized_w,
+                     float* tokens_out, void* stream, bool flip_tta) {
+  const int batch = flip_tta ? 2 * src_batch : src_batch;
   WVN_REQUIRE(h && img, "wvn_vit_forward: null argument");
   WVN_REQUIRE(batch > 0 && batch <= h->cfg.max_batch, "wvn_vit_forward: batch %d outside (0, %d]", batch, h->cfg.max_batch);
   WVN_REQUIRE(resized_h >= h->cfg.image_size && resized_w >= h->cfg.image_size,
@@ -358,8 +366,8 @@ int vit_forward_impl(wvn_vit_t* h, const void* img, bool u8_hwc, int batch, int 
     const int rows = nb * h->npad;
     float* x = reinterpret_cast<float*>(h->x.p);
     ia.batch = nb;
-    const long long frame_bytes = static_cast<long long>(3) * in_h * in_w * (u8_hwc ? 1 : 4);
-    WVN_PROPAGATE(image_to_patches(static_cast<const char*>(img) + b0 * frame_bytes, u8_hwc, h->ape.p, ia, s));
+    ia.frame0 = b0; ia.src_frames = src_batch; ia.flip_from = flip_tta ? src_batch : (1 << 30);
+    WVN_PROPAGATE(image_to_patches(img, u8_hwc, h->ape.p, ia, s));
     WVN_PROPAGATE(init_token_rows(x, h->wp<float>("cls_token"), h->wp<float>("pos_embed"), nb, h->npad, h->n_valid, D, s));
     {
       GemmArgs g;

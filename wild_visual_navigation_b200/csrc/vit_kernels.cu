@@ -45,12 +45,17 @@ __global__ void image_to_patches_kernel(const void* __restrict__ img_raw, __nv_b
     // torch 'nearest': src = min(floor(dst * scale), in - 1), scale = in / out in fp32
     const int sy = min(static_cast<int>(floorf((y + a.crop_top) * a.scale_y)), a.in_h - 1);
     const float mean = a.mean[c], inv_std = a.inv_std[c];
-    const float* src_row = img + ((static_cast<long long>(b) * 3 + c) * a.in_h + sy) * a.in_w;
-    const unsigned char* src_row8 = img8 + (static_cast<long long>(b) * a.in_h + sy) * a.in_w * 3 + c;
+    const int gb = a.frame0 + b;
+    const bool flip = gb >= a.flip_from;
+    const int sb = gb % a.src_frames;
+    const int crop_w = a.grid_w * ps;
+    const float* src_row = img + ((static_cast<long long>(sb) * 3 + c) * a.in_h + sy) * a.in_w;
+    const unsigned char* src_row8 = img8 + (static_cast<long long>(sb) * a.in_h + sy) * a.in_w * 3 + c;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int x = pw * ps + kx0 + i;
+      const int xo = pw * ps + kx0 + i;
+      const int x = flip ? crop_w - 1 - xo : xo;
       const int sx = min(static_cast<int>(floorf((x + a.crop_left) * a.scale_x)), a.in_w - 1);
       // uint8: the same IEEE division torchvision's ToTensor performs, so both sources give identical patches
       const float px = U8_HWC ? static_cast<float>(__ldg(src_row8 + 3 * sx)) / 255.f : __ldg(src_row + sx);

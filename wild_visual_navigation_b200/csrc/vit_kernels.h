@@ -12,6 +12,10 @@ struct ImagePatchArgs {
   int grid_h = 0, grid_w = 0;    // patches per column / row of the cropped image
   int crop_top = 0, crop_left = 0;  // center-crop offsets in the (virtually) resized image
   float scale_y = 1.f, scale_x = 1.f;  // in / resized (torch 'nearest' source index scale)
+  // Test-time-augmentation passes: output frame f reads source frame (frame0 + f) % src_frames, and frames with
+  // frame0 + f >= flip_from are the horizontal flip of the TRANSFORMED (resized + cropped) image, as Stego.get_code
+  // flips its already-transformed input.  Defaults = identity.
+  int frame0 = 0, src_frames = 1 << 30, flip_from = 1 << 30;
   float mean[3] = {0.485f, 0.456f, 0.406f};
   float inv_std[3] = {1.f / 0.229f, 1.f / 0.224f, 1.f / 0.225f};
 };

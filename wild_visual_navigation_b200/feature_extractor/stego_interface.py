@@ -72,9 +72,9 @@ class StegoInterface:
         vit = self._dino._model
         g, npad = vit.grid, vit.npad
         if self._flip_tta:
-            # Stego.get_code: average with the horizontally flipped pass (flip back at patch level)
-            both = torch.cat([img, img.flip(dims=[3])], dim=0)
-            tokens = vit.forward(both)
+            # Stego.get_code: average with the pass over the horizontally flipped TRANSFORMED image (the flip happens
+            # inside the patch loader, after resize + crop); flip back at patch level
+            tokens = vit.forward(img, flip_tta=True)
             out = vit.stego_head(2 * B).view(2, B, npad, -1)
             a = out[0, :, 1 : 1 + g * g].reshape(B, g, g, -1)
             b = out[1, :, 1 : 1 + g * g].reshape(B, g, g, -1).flip(dims=[2])

@@ -176,11 +176,16 @@ class ViTBackbone:
         self._set("norm.weight", sd["norm.weight"])
         self._set("norm.bias", sd["norm.bias"])
 
-    def forward(self, img: torch.Tensor, resized_hw=None) -> torch.Tensor:
+    def forward(self, img: torch.Tensor, resized_hw=None, flip_tta: bool = False) -> torch.Tensor:
         """img: (B,3,H,W) f32 CUDA in [0,1], or the camera frames themselves (B,H,W,3) uint8 RGB
-        -> final-norm patch tokens (B, P, D) f32."""
+        -> final-norm patch tokens (B, P, D) f32.  flip_tta (float input only): (2B, P, D), the second half being the
+        pass over the horizontally flipped TRANSFORMED images (STEGO's get_code)."""
         img = img.contiguous()
-        if img.dtype == torch.uint8:
+        if flip_tta:
+            B, C, H, W = img.shape
+            assert img.dtype == torch.float32
+            fn = lib().wvn_vit_forward_tta
+        elif img.dtype == torch.uint8:
             B, H, W, C = img.shape
             fn = lib().wvn_vit_forward_u8
         else:
@@ -190,7 +195,7 @@ class ViTBackbone:
         assert C == 3
         if resized_hw is None:
             resized_hw = _resized_size(H, W, self.image_size)
-        tokens = torch.empty(B, self.P, self.dim, device=img.device, dtype=torch.float32)
+        tokens = torch.empty(2 * B if flip_tta else B, self.P, self.dim, device=img.device, dtype=torch.float32)
         check(fn(self._h, ptr(img), B, H, W, resized_hw[0], resized_hw[1], ptr(tokens), stream()))
         return tokens
 
