@@ -17,6 +17,8 @@ Fixtures
   tmp_state_dict.pt the weight hand-off file as wvn_learning_node.py:381-394 writes it (reference SimpleMLP + ConfidenceGenerator)
   segments.npz      reference SegmentExtractor on a synthetic map + the reference's shipped
                     known-answer assets/graph/{seg,center}.pt and graph.pt edge_index
+  extract_stego.pt  reference FeatureExtractor.extract end to end (stego segmentation + stego features) over the
+                    shimmed StegoInterface and the reference SegmentExtractor
   stego_wrapper.pt  reference StegoInterface.inference (its real transform / interpolation code) around a shim Stego
                     model made of the oracle's restated head + backbone (tiny config)
   dino_wrapper.pt   reference DinoInterface.inference (its real transform / upsample code) wrapped
@@ -298,7 +300,27 @@ def make_dino_wrapper():
                os.path.join(HERE, "dino_wrapper.pt"))
 
 
-def make_stego_wrapper():
+def make_extract(ns, stego_interface, cfg):
+    """End to end: the reference's OWN ``FeatureExtractor.extract`` orchestration (extract / compute_segments /
+    segment_stego / compute_features / compute_stego / sparsify_features, feature_extractor.py:95-128,151-177,237-271,
+    310-398 — method sources compiled from the reference file) over the reference's StegoInterface (shimmed external
+    nets) and the reference's SegmentExtractor, configuration segmentation_type = feature_type = "stego"."""
+    fe = "wild_visual_navigation/feature_extractor/feature_extractor.py"
+    names = ["extract", "compute_segments", "segment_stego", "compute_features", "compute_stego", "sparsify_features"]
+    cls = type("RefFeatureExtractor", (), {n: _reference_method(fe, n) for n in names})
+    me = cls()
+    me._device, me._segmentation_type, me._feature_type, me._input_size = "cpu", "stego", "stego", cfg.image_size
+    me._stego_features_already_computed_in_segmentation = False
+    me.segment_extractor = ns.SegmentExtractor()
+    me._extractor = stego_interface
+    g = torch.Generator().manual_seed(12)
+    img = torch.rand(1, 3, 32, 32, generator=g)
+    edges, feat, seg, center, dense = me.extract(img, return_dense_features=True)
+    torch.save({"img": img, "edges": edges, "feat": feat, "seg": seg, "center": center, "dense": dense},
+               os.path.join(HERE, "extract_stego.pt"))
+
+
+def make_stego_wrapper(ns):
     """The reference's own ``StegoInterface.inference`` (stego_interface.py:73-111: transform, code -> bilinear
     align_corners=True to (H, H), predictions -> nearest (H, H) int, return order) around a shim ``Stego`` model whose
     ``get_code`` / ``postprocess`` are the oracle's restated head on the oracle's restated backbone."""
@@ -339,6 +361,7 @@ def make_stego_wrapper():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     si = mod.StegoInterface(device="cpu", input_size=32, n_image_clusters=6, run_crf=False, run_clustering=False)
+    make_extract(ns, si, cfg)
     g = torch.Generator().manual_seed(10)
     img = torch.rand(2, 3, 40, 52, generator=g)  # non-square: the transform resizes (NEAREST) and crops
     linear, cluster = si.inference(img.clone())
@@ -360,6 +383,6 @@ if __name__ == "__main__":
     make_sparsify()
     make_segments(ns)
     make_dino_wrapper()
-    make_stego_wrapper()
+    make_stego_wrapper(ns)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

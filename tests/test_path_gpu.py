@@ -146,6 +146,42 @@ def test_stego_head_and_segments(flip_tta, hw):
     assert agree_c >= 0.98 and agree_l >= 0.98
 
 
+def test_feature_extractor_extract_contract_vs_oracle(golden_dir):
+    """``FeatureExtractor.extract`` (stego segmentation + stego features, the reference's supported pairing): the
+    returned tuple has the contract the reference's own extract produces (extract_stego.pt: edges (2,E) int64, feat
+    (S,90), seg (H,W), center (S,2), dense (1,90,H,H)) and its values match the oracle chain — which test_oracle.py
+    holds to that same reference golden — at ViT-S/8 224."""
+    from oracle import stego_head, wvn_path
+    from oracle.dino_vit import ViTConfig, synthetic_state_dict, vit_feature_map
+    from wild_visual_navigation_b200.feature_extractor import FeatureExtractor
+
+    ref = torch.load(os.path.join(golden_dir, "extract_stego.pt"))
+    cfg = ViTConfig.from_name("vit_small", 8, 224)
+    sd = synthetic_state_dict(cfg, seed=6)
+    hd = stego_head.synthetic_head(384, 90, 32, 27, seed=3)
+    fe = FeatureExtractor("cuda", segmentation_type="stego", feature_type="stego", input_size=224, state_dict=sd,
+                          head_state_dict=hd, flip_tta=True, max_batch=2)
+    img = torch.rand(1, 3, 224, 224, generator=torch.Generator().manual_seed(8)).cuda()
+    edges, feat, seg, center, dense = fe.extract(img, return_dense_features=True)
+    assert fe.feature_dim == 90 and fe.feature_type == "stego" and fe.segmentation_type == "stego"
+    S = int(seg.max()) + 1
+    assert edges.dtype == ref["edges"].dtype and edges.shape[0] == 2 and feat.shape == (S, 90) and center.shape == (S, 2)
+    assert seg.shape == (224, 224) and dense.shape == (1, 90, 224, 224)
+    sdc, hdc = _to(sd, "cuda"), _to(hd, "cuda")
+    t = wvn_path.wvn_transform(img, 224)
+    f, ff = vit_feature_map(t, sdc, cfg), vit_feature_map(t.flip(dims=[3]), sdc, cfg)
+    code_up, cluster, _ = stego_head.stego_inference(f, ff, hdc, (224, 224))
+    seg_ref = wvn_path.relabel(cluster[0].long())
+    agree = (seg == seg_ref).float().mean().item()
+    print("extract: segment agreement", agree, "dense rel_l2", rel_l2(dense, code_up))
+    assert agree >= 0.98 and rel_l2(dense, code_up) <= 3e-2
+    # on OUR segmentation the pooled features / centers / edges must equal the reference's definitions exactly
+    feat_ref = wvn_path.sparsify_features(dense, seg)
+    assert (feat - feat_ref).abs().max() <= 2e-3 * feat_ref.abs().max()
+    assert (center - wvn_path.centers(seg[None, None])).abs().max() < 1e-3
+    assert torch.equal(edges, wvn_path.adjacency_list(seg[None, None]).T)
+
+
 def test_segment_known_answer_asset(golden_dir):
     """Reference's shipped fixture: centers(seg.pt) == center.pt, adjacency == graph.pt edge_index."""
     from wild_visual_navigation_b200.feature_extractor import SegmentExtractor
