@@ -66,6 +66,76 @@ def test_vit_tokens_parity_448(vit448):
     assert torch.equal(alone[0], got[2])
 
 
+def test_vit_base_tokens_parity_512():
+    """BASELINE.json config 5's model family: DINO ViT-B/8 (D 768, 12 heads) on a 64x64 token grid (512 px; 518 floors
+    to the same grid), single frame, against the fp32 oracle."""
+    from oracle.dino_vit import ViTConfig, synthetic_state_dict, vit_tokens
+    from oracle.wvn_path import wvn_transform
+    from wild_visual_navigation_b200.feature_extractor import DinoInterface
+
+    cfg = ViTConfig.from_name("vit_base", 8, 512)
+    # qkv std scaled by 1/sqrt(2) against the ViT-S fixtures so that the attention logits keep a realistic spread
+    # (std ~3, max ~20) at D = 768; at the default std they are ~6 / 40 — a near one-hot softmax in which the bf16
+    # rounding of q.k alone moves the weights by > 10 %, which says nothing about the kernels
+    sd = synthetic_state_dict(cfg, seed=2, attn_std=0.09 / 2 ** 0.5)
+    di = DinoInterface("cuda", input_size=512, backbone_type="vit_base", patch_size=8, state_dict=sd, max_batch=2)
+    img = torch.rand(2, 3, 512, 512, generator=torch.Generator().manual_seed(1)).cuda()
+    got = di.inference_tokens(img)
+    ref = vit_tokens(wvn_transform(img, 512), _to(sd, "cuda"), cfg)
+    assert got.shape == ref.shape == (2, 4096, 768)
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=-1)
+    print("vit-b 512 rel_l2", rel_l2(got, ref), "cos min/mean", cos.min().item(), cos.mean().item())
+    assert rel_l2(got, ref) <= 2e-2 and cos.mean() >= 0.999 and cos.min() >= 0.99
+
+
+def test_beats_eager_gpu_reference_path():
+    """North star: "end-to-end frames/s at 1 GPU that beats the reference's own GPU PyTorch path on the same B200".
+    The oracle IS that path (eager fp32 PyTorch in the reference's order of operations); it is timed here on the GPU
+    for the backbone + per-pixel inference of 448x448 frames next to the product.  Prints both; asserts >= 5x."""
+    import time
+
+    from oracle import pipeline, wvn_path
+    from oracle.dino_vit import ViTConfig, synthetic_state_dict
+    from wild_visual_navigation_b200 import TraversabilityInference, get_model
+    from wild_visual_navigation_b200.feature_extractor import DinoInterface
+    from wild_visual_navigation_b200.utils import ConfidenceGenerator
+
+    cfg = ViTConfig.from_name("vit_small", 8, 448)
+    sd = synthetic_state_dict(cfg, seed=1)
+    B = 8
+    di = DinoInterface("cuda", input_size=448, backbone_type="vit_small", patch_size=8, state_dict=sd, max_batch=B)
+    torch.manual_seed(42)
+    model = get_model({"name": "SimpleMLP", "simple_mlp_cfg": {"input_size": 384, "hidden_sizes": [256, 32, 1],
+                                                               "reconstruction": True}}).cuda()
+    cg = ConfidenceGenerator(std_factor=0.5, method="latest_measurement").cuda()
+    ti = TraversabilityInference(di, model, cg)
+    img = torch.rand(B, 3, 448, 448, generator=torch.Generator().manual_seed(0)).cuda()
+    sdc = _to(sd, "cuda")
+    mlp_sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    def eager(frames):
+        for b in range(frames):
+            f = pipeline.frame_features(img[b : b + 1], sdc, cfg, None)
+            wvn_path.pixel_inference(f["dense"], mlp_sd, cg.mean.data, cg.std.data, 0.5)
+
+    def ours():
+        ti.predict(img)
+
+    def timed(fn, *a):
+        fn(*a)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn(*a)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    t_eager = timed(eager, 2) / 2
+    t_ours = timed(ours) / B
+    print(f"eager fp32 PyTorch on this GPU: {1 / t_eager:.1f} frames/s ({t_eager * 1e3:.1f} ms/frame);  "
+          f"wvn-b200 (ViT + per-pixel MLP, B={B}): {1 / t_ours:.1f} frames/s;  speed-up {t_eager / t_ours:.1f}x")
+    assert t_eager / t_ours >= 5.0
+
+
 def test_dino_interface_dense_with_resize():
     """Non-square input that needs the NEAREST resize + center crop, vit_small/8 at 224."""
     from oracle.dino_vit import ViTConfig, synthetic_state_dict
