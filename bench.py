@@ -280,7 +280,7 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    lib.wvn_profile_enable(1)
+    lib.wvn_profile_enable(3 if args.profile_gemm else 1)   # CUDA events around the roofline kernel's launches
     l0 = lib.wvn_launch_count()
     total_ms = timed(lambda k: step(dev_imgs[k % 3]), args.steps)
     launches = lib.wvn_launch_count() - l0
@@ -329,8 +329,8 @@ def run_b200(args):
                      "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside the step)",
                      "traffic": traffic, "avg_launch_ms": attn_avg_ms, "launches": int(prof_n[0]),
                      "share_of_step": prof_ms[0] / total_ms if total_ms > 0 else None,
-                     "gemm_share_of_step": prof_ms[1] / total_ms if total_ms > 0 else None,
-                     "gemm_launches": int(prof_n[1])},
+                     "gemm_share_of_step": prof_ms[1] / total_ms if (total_ms > 0 and prof_n[1] > 0) else None,
+                     "gemm_launches": int(prof_n[1]) if prof_n[1] > 0 else None},
         "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{args.cpu_frames} frame(s), one full step of the oracle port (eager fp32 torch, all host threads)"},
         "whole_path_tflops": value * (315.1 + 1.36 + 47.69) / 1000.0,
@@ -352,6 +352,8 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=32,
                     help="torch CPU threads for the CPU legs (more than ~32 only adds sync overhead on these small ops)")
     ap.add_argument("--profile-only", action="store_true", help="setup + warmup + steps only (for ncu)")
+    ap.add_argument("--profile-gemm", action="store_true",
+                    help="also time every GEMM launch with CUDA events (gemm_share_of_step; ~280 extra event pairs per step)")
     ap.add_argument("--ingest", default="f32", choices=["f32", "u8"],
                     help="frame format at the boundary: f32 = (B,3,H,W) float in [0,1] (the reference's boundary, "
                          "BASELINE.json); u8 = camera frames (B,H,W,3) uint8, ingest fused into the patch loader (SURVEY.md §8f)")

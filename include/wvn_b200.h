@@ -47,9 +47,11 @@ int wvn_version(void);
 /* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */
 long long wvn_launch_count(void);
 /* Optional CUDA-event timing of the dominant kernels inside real steps (bench.py roofline):
- * category 0 = fused attention, 1 = tcgen05 GEMMs.  collect() synchronises and writes the summed
- * milliseconds / launch counts per category into HOST arrays of length 2 and clears the records. */
-void wvn_profile_enable(int on);
+ * category 0 = fused attention, 1 = tcgen05 GEMMs; category_mask bit c enables category c (0 = off, 1 = the
+ * roofline kernel only — 24 event pairs per step —, 3 = attention + the ~280 GEMM launches per step).
+ * collect() synchronises and writes the summed milliseconds / launch counts per category into HOST arrays of
+ * length 2 and clears the records. */
+void wvn_profile_enable(int category_mask);
 int wvn_profile_collect(float* host_ms, long long* host_launches);
 
 /* ------------------------------------------------------------------------------------------

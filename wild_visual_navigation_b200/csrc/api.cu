@@ -120,7 +120,7 @@ int wvn_check_device(void) {
 }
 
 long long wvn_launch_count(void) { return launch_count(); }
-void wvn_profile_enable(int on) { prof_enable(on != 0); }
+void wvn_profile_enable(int category_mask) { prof_enable(category_mask); }
 int wvn_profile_collect(float* host_ms, long long* host_launches) {
   WVN_REQUIRE(host_ms && host_launches, "wvn_profile_collect: null argument");
   return prof_collect(host_ms, host_launches);

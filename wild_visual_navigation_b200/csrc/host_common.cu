@@ -102,7 +102,7 @@ long long launch_count() { return g_launches.load(); }
 namespace {
 struct ProfRec { int cat; cudaEvent_t a, b; };
 std::mutex g_prof_mu;
-bool g_prof_on = false;
+int g_prof_mask = 0;  // bit c = category c is timed
 std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_pool;
 cudaEvent_t g_open[PROF_NUM] = {nullptr, nullptr};
@@ -114,21 +114,21 @@ cudaEvent_t get_event() {
 }
 }  // namespace
 
-void prof_enable(bool on) {
+void prof_enable(int category_mask) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  g_prof_on = on;
+  g_prof_mask = category_mask;
 }
 
 void prof_begin(int cat, cudaStream_t s) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  if (!g_prof_on) return;
+  if (!((g_prof_mask >> cat) & 1)) return;
   g_open[cat] = get_event();
   cudaEventRecord(g_open[cat], s);
 }
 
 void prof_end(int cat, cudaStream_t s) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  if (!g_prof_on || g_open[cat] == nullptr) return;
+  if (g_open[cat] == nullptr) return;
   cudaEvent_t b = get_event();
   cudaEventRecord(b, s);
   g_prof.push_back({cat, g_open[cat], b});

@@ -65,7 +65,7 @@ int sm_count();
 void count_launch();
 long long launch_count();
 enum ProfCategory : int { PROF_ATTENTION = 0, PROF_GEMM = 1, PROF_NUM = 2 };
-void prof_enable(bool on);
+void prof_enable(int category_mask);
 void prof_begin(int cat, cudaStream_t s);
 void prof_end(int cat, cudaStream_t s);
 // Synchronises, sums elapsed ms per category, clears the record list.
