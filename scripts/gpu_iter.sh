@@ -2,12 +2,6 @@
 # iteration script (rewritten per experiment)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-for pg in "" "--profile-gemm" "" "--profile-gemm"; do
-timeout 600 python bench.py --steps 10 --warmup 3 --cpu-frames 0 $pg 2> gpurun_out/bench_iter.err | python -c "
-import sys, json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d = json.loads(l); r = d['roofline']
-        print('[$pg] fps', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'attn TF', round(r['achieved'],1), 'attn share', round(r['share_of_step'],3), 'gemm share', r['gemm_share_of_step'])
-"
-done
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 2500 gpurun_out/bench_default.json; tail -2 gpurun_out/bench_default.err
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -2
