@@ -2,6 +2,4 @@
 # iteration script (rewritten per experiment)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
-timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 2500 gpurun_out/bench_default.json; tail -2 gpurun_out/bench_default.err
-timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4

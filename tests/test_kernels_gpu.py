@@ -118,6 +118,29 @@ def test_upsample_dense_matches_torch(ops):
     assert (out - ref).abs().max() < 1e-5
 
 
+def test_logits_argmax_pruned_candidates_two_ranges(ops):
+    """Spatially smooth logits (1-3 classes can win per interpolation cell -> the candidate-pruned path) for two probe
+    ranges resolved in one pass, against torch's upsample + argmax."""
+    B, g, npad, Ka, Kb = 3, 28, 896, 32, 27
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    yy, xx = torch.meshgrid(torch.arange(g, device="cuda").float(), torch.arange(g, device="cuda").float(), indexing="ij")
+    def field(K):
+        cy = torch.rand(B, K, generator=gen, device="cuda") * g
+        cx = torch.rand(B, K, generator=gen, device="cuda") * g
+        d = (yy[None, None] - cy[:, :, None, None]) ** 2 + (xx[None, None] - cx[:, :, None, None]) ** 2
+        return (-d / 20 + 0.05 * torch.randn(B, K, g, g, generator=gen, device="cuda")).permute(0, 2, 3, 1)  # (B,g,g,K)
+    fa, fb = field(Ka), field(Kb)
+    logits = torch.zeros(B * npad, 128, device="cuda")
+    v = logits.view(B, npad, 128)
+    v[:, 1 : 1 + g * g, 8 : 8 + Ka] = fa.reshape(B, g * g, Ka)
+    v[:, 1 : 1 + g * g, 64 : 64 + Kb] = fb.reshape(B, g * g, Kb)
+    sa, sb = ops.logits_argmax(logits, 8, Ka, B, npad, g, g, 224, 224, col0_b=64, classes_b=Kb)
+    for got, f in ((sa, fa), (sb, fb)):
+        ref = torch.nn.functional.interpolate(f.permute(0, 3, 1, 2), (224, 224), mode="bilinear", align_corners=False).argmax(1)
+        agree = (got == ref).float().mean().item()
+        assert agree > 0.9995, agree
+
+
 def test_logits_argmax_matches_upstream_order(ops):
     """argmax(bilinear_upsample(logits)) == argmax(probe(bilinear_upsample(code)))."""
     B, g, K, npad = 2, 7, 11, 128
