@@ -134,11 +134,13 @@ int wvn_gemm_bf16(const void* a, long long lda, const void* w, const float* bias
   g.epi = out_kind == 0 ? EPI_BF16 : (out_kind == 1 ? EPI_F32 : EPI_RESID_F32);
   WVN_REQUIRE(out_kind >= 0 && out_kind <= 2, "wvn_gemm_bf16: out_kind %d", out_kind);
   g.act = act; g.bias = bias; g.out = out; g.ldo = ldo;
+#ifdef WVN_GEMM_ABLATE
   {
-    static int dbg = -1;  // $WVN_GEMM_DEBUG: kernel experiments only (1 = no stores, 2 = no epilogue); never set in production
+    static int dbg = -1;  // $WVN_GEMM_DEBUG: epilogue ablations (1 = no stores, 2 = no epilogue), ablation builds only
     if (dbg < 0) { const char* e = getenv("WVN_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
     g.debug = dbg;
   }
+#endif
 #ifdef WVN_GEMM_TIMING
   static long long* tbuf = nullptr;  // device memory: the probes must not fault on managed pages
   if (!tbuf) cudaMalloc(&tbuf, 8 * sizeof(long long));

@@ -102,7 +102,13 @@ __device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
   x1 = fmaf(-t1, e1, fmaxf(x1, 0.f));
 }
 
-#define WVN_DBG_STORE && args.debug != 1  // experiment knob ($WVN_GEMM_DEBUG through wvn_gemm_bf16): 1 = no global stores
+// Epilogue ablations exist only in `make ablate` / `make timing` builds: $WVN_GEMM_DEBUG = 1 skips the
+// global stores, 2 drops the accumulators.  The shipped library has no such switch.
+#ifdef WVN_GEMM_ABLATE
+#define WVN_DBG_STORE && args.debug != 1
+#else
+#define WVN_DBG_STORE
+#endif
 
 // One 128 x BN accumulator tile: TMEM -> registers -> bias / activation -> global memory.  Called by the kEpiWarps
 // epilogue warps (ewarp & 3 must equal the hardware warp's TMEM lane quarter); the kEpiGroups warps of a lane
@@ -129,7 +135,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
     tok = row - frame * args.npad;
   }
 
-  if (args.debug == 2) return;  // experiment knob: accumulators are dropped
+#ifdef WVN_GEMM_ABLATE
+  if (args.debug == 2) return;
+#endif
 #pragma unroll
   for (int chunk_i = 0; chunk_i < kChunksPerThread; ++chunk_i) {
     const int c0 = 32 * (group + kEpiGroups * chunk_i);
