@@ -66,3 +66,20 @@ def test_reference_classes_load_our_file(tmp_path):
         assert torch.equal(v, model.state_dict()[name])
     c = new_model_state_dict["confidence_generator"]
     assert abs(c["mean"].item() - 0.11) < 1e-7 and abs(c["std"].item() - 0.07) < 1e-7 and tuple(c["var"].shape) == (1, 1)
+
+
+def test_image_features_wire_roundtrip():
+    """ImageFeatures.msg field layout (wvn_feature_extractor_node.py:373-393) and the learning node's decode
+    (wvn_learning_node.py:651-656): bit-identical round trip."""
+    from wild_visual_navigation_b200.utils import decode_image_features, encode_image_features
+
+    g = torch.Generator().manual_seed(4)
+    feat = torch.randn(7, 90, generator=g) * 3
+    seg = torch.randint(0, 7, (24, 32), generator=g)
+    msg = encode_image_features(feat, seg, header={"seq": 5, "frame_id": "cam"})
+    dim = msg["features"]["layout"]["dim"]
+    assert [(d["label"], d["size"], d["stride"]) for d in dim] == [("n", 7, 630), ("feat", 90, 90)]
+    assert isinstance(msg["features"]["data"], list) and len(msg["features"]["data"]) == 630
+    assert msg["feature_segments"]["step"] == 32 * 4 and len(msg["feature_segments"]["data"]) == 24 * 32 * 4
+    f2, s2 = decode_image_features(msg)
+    assert torch.equal(f2, feat) and torch.equal(s2.long(), seg) and s2.dtype == torch.int32
