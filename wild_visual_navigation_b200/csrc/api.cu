@@ -380,9 +380,9 @@ int vit_forward_impl(wvn_vit_t* h, const void* img, bool u8_hwc, int src_batch, 
     LayerNormArgs la;
     la.rows = rows; la.dim = D; la.eps = c.ln_eps; la.npad = h->npad; la.n_valid = h->n_valid;
     // GEMMs / LayerNorms can run over sub-chunks of `sub` frames ($WVN_VIT_SUBCHUNK) to keep xn / hid / x
-    // L2-resident between producer and consumer, while attention always covers the whole chunk.  Measured
-    // on B200 (round 1): sub-chunking LOSES (1631 / 1563 / 1453 / 1253 frames/s at sub = 32 / 16 / 8 / 4) —
-    // the skinny-K GEMMs are bound by the per-SM L2->smem ingest rate, not by DRAM — so the default is off.
+    // L2-resident between producer and consumer.  Measured on B200 (round 1): sub-chunking LOSES (1752 -> 1719
+    // frames/s at sub = 16): what the smaller GEMMs lose to wave quantisation (the N = 384 GEMMs drop to 5.4 waves)
+    // outweighs the L2 hits, which the snake order below already collects for the hottest ~100 MB — default off.
     static int sub_env = -1;
     if (sub_env < 0) {
       const char* e = getenv("WVN_VIT_SUBCHUNK");
