@@ -35,13 +35,6 @@ namespace wvn {
 namespace {
 
 constexpr int kThreads = 192;
-// waits of the single-thread MMA issuer (experiment: -DWVN_SPIN_WAIT busy-polls instead of try_wait)
-#ifdef WVN_SPIN_WAIT
-#define WVN_CRIT_WAIT(bar, par) mbar_wait_spin(bar, par)
-#else
-#define WVN_CRIT_WAIT(bar, par) mbar_wait(bar, par)
-#endif
-
 constexpr int kTileQ = 128;
 constexpr int kTileKV = 128;
 constexpr int kDh = 64;
@@ -305,8 +298,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       auto issue_qk = [&](int j) {
         const int st = j % kStages;
         const uint32_t ph = (j / kStages) & 1;
-        WVN_CRIT_WAIT(&k_full[st], ph);
-        if (j > 0) WVN_CRIT_WAIT(s_free, (j - 1) & 1);  // softmax has drained S(j-1) from TMEM
+        mbar_wait(&k_full[st], ph);
+        if (j > 0) mbar_wait(s_free, (j - 1) & 1);  // softmax has drained S(j-1) from TMEM
         tc_fence_after();
         const uint64_t desc_k = make_sw128_kmajor_desc(smem_u32(smem + kOffK + st * kKBytes));
 #pragma unroll
@@ -335,9 +328,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         WVN_TM(0)
         const int st = j % kStages;
         const uint32_t ph = (j / kStages) & 1;
-        WVN_CRIT_WAIT(p_full, j & 1);
+        mbar_wait(p_full, j & 1);
         WVN_TM(1)
-        WVN_CRIT_WAIT(&v_full[st], ph);
+        mbar_wait(&v_full[st], ph);
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem + kOffV + st * kVBytes);
 #pragma unroll

@@ -83,41 +83,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Non-blocking probe of the phase (never suspends the thread, unlike try_wait).
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-
 // Bounded wait: a protocol bug must surface as a trapped kernel (an error code on the
 // host), never as a hung GPU.  ~4e9 SM cycles ≈ 2 s at boost clocks.
 #ifndef WVN_MBAR_TIMEOUT_CYCLES
 #define WVN_MBAR_TIMEOUT_CYCLES 4000000000ll
 #endif
-
-// Same contract as mbar_wait, but busy-polls with test_wait: for the single-thread roles on a kernel's critical path
-// (MMA issuer, TMA producer), where try_wait's suspend / wake-up granularity would be paid on every pipeline step.
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-  if (mbar_test_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_test_wait(bar, parity)) {
-    if ((++spins & 0xfff) == 0 && clock64() - t0 > WVN_MBAR_TIMEOUT_CYCLES) {
-      printf("[wvn] mbarrier timeout (spin): block (%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
-  }
-}
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;

@@ -273,13 +273,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
     }
   }
 }
-// waits of the two single-thread pipeline roles (experiment: -DWVN_SPIN_WAIT busy-polls instead of try_wait)
-#ifdef WVN_SPIN_WAIT
-#define WVN_CRIT_WAIT(bar, par) mbar_wait_spin(bar, par)
-#else
-#define WVN_CRIT_WAIT(bar, par) mbar_wait(bar, par)
-#endif
-
 #ifdef WVN_GEMM_TIMING
 #define WVN_TM_DECL const bool timing = args.timing != nullptr && blockIdx.x == 0; long long tm[4] = {0, 0, 0, 0}, tprev = clock64(), ntiles = 0;
 #define WVN_TM(i) if (timing) { const long long tn = clock64(); tm[i] += tn - tprev; tprev = tn; }
@@ -352,7 +345,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (TileIter<ROW_OWNER> it(num_m, num_n); it.valid(); it.next()) {
         const int m_eff = args.reverse_m ? num_m - 1 - it.m_blk : it.m_blk;
         for (int kb = 0; kb < num_k; ++kb) {
-          WVN_CRIT_WAIT(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * BK, m_eff * BM);
           tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * BK, it.n_blk * BN);
@@ -370,12 +363,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t acc_phase = 0;
       WVN_TM_DECL
       for (TileIter<ROW_OWNER> it(num_m, num_n); it.valid(); it.next()) {
-        WVN_CRIT_WAIT(&acc_empty[acc], acc_phase ^ 1);
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         WVN_TM(0)
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k; ++kb) {
-          WVN_CRIT_WAIT(&full_bar[stage], phase);
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           WVN_TM(1)
           const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
