@@ -1,5 +1,6 @@
 #!/bin/bash
-# iteration script (rewritten per experiment)
+# iteration script (rewritten per experiment): the round-end verification
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
