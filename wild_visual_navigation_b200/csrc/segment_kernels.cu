@@ -158,10 +158,93 @@ segment_accumulate_tiled_kernel(const long long* __restrict__ seg, SegmentArgs a
   }
 }
 
-// feat_sum[b][s][d] += sum_p W[b][s][p] * tok[b][p][d]   (small dense GEMM; W is segments x tokens)
-// grid (ceil(dim/64), ceil(smax/32), B * ksplit); 256 threads: thread -> column tx, 8 rows.
+// feat_sum[b][s][d] += sum_p W[b][s][p] * tok[b][p][d]   (small dense GEMM; W is segments x tokens).
+// The token matrix (154 MB for 32 frames) is read exactly once, with 16-byte loads: CTA = (frame, 32-segment block,
+// token range); per 32-token step the W tile [32 seg][32 tok] and the token tile [32 tok][dim] are staged in shared
+// memory; warp w owns segments 4w..4w+3, lane l owns float4 columns l, l+32, l+64 (dim <= 384) — 48 accumulators,
+// 3 + 4 shared loads per 48 FMAs; wider features (ViT-B: 768) take one CTA column block of 384 each (blockIdx.x).
+// Partial sums are flushed with vector atomics (ksplit CTAs per output block).
+constexpr int kPoolTok = 32;      // tokens per step
+constexpr int kPoolMaxV4 = 3;     // float4 column groups per lane: dim <= 384
+
 __global__ void __launch_bounds__(256)
 segment_pool_gemm_kernel(const float* __restrict__ wseg, const float* __restrict__ tok, float* __restrict__ feat,
+                         SegmentArgs a, int ksplit) {
+  extern __shared__ float4 pool_sm[];                       // [kPoolTok][dim/4] token tile, then [32][kPoolTok+1] W tile
+  const int row_v4 = a.dim / 4;                              // float4 per token row
+  const int c_base = blockIdx.x * 32 * kPoolMaxV4;           // first float4 column of this CTA's block
+  const int dv4 = min(32 * kPoolMaxV4, row_v4 - c_base);     // float4 columns handled here
+  float4* Ts = pool_sm;
+  float* Ws = reinterpret_cast<float*>(pool_sm + kPoolTok * 32 * kPoolMaxV4);
+  const int P = a.grid_h * a.grid_w;
+  const long long b = blockIdx.z / ksplit;
+  const int split = blockIdx.z % ksplit;
+  const int kper = ((P + ksplit - 1) / ksplit + kPoolTok - 1) / kPoolTok * kPoolTok;
+  const int k_beg = split * kper, k_end = min(P, k_beg + kper);
+  const int s0 = blockIdx.y * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 acc[4][kPoolMaxV4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < kPoolMaxV4; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* wb = wseg + (b * a.smax) * P;
+  const float4* tb = reinterpret_cast<const float4*>(tok + b * P * a.dim);
+  for (int k0 = k_beg; k0 < k_end; k0 += kPoolTok) {
+    for (int i = threadIdx.x; i < 32 * kPoolTok; i += 256) {
+      const int r = i / kPoolTok, k = i % kPoolTok;
+      Ws[r * (kPoolTok + 1) + k] =
+          (s0 + r < a.smax && k0 + k < k_end) ? __ldg(wb + static_cast<long long>(s0 + r) * P + k0 + k) : 0.f;
+    }
+    for (int i = threadIdx.x; i < kPoolTok * dv4; i += 256) {
+      const int k = i / dv4, c = i - k * dv4;
+      Ts[i] = (k0 + k < k_end) ? __ldg(tb + static_cast<long long>(k0 + k) * row_v4 + c_base + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < kPoolTok; ++k) {
+      float w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = Ws[(warp * 4 + i) * (kPoolTok + 1) + k];
+      if (w[0] == 0.f && w[1] == 0.f && w[2] == 0.f && w[3] == 0.f) continue;  // W is sparse: most tokens touch few segments
+#pragma unroll
+      for (int j = 0; j < kPoolMaxV4; ++j) {
+        const int c = lane + 32 * j;
+        if (c < dv4) {
+          const float4 t = Ts[k * dv4 + c];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i][j].x = fmaf(w[i], t.x, acc[i][j].x);
+            acc[i][j].y = fmaf(w[i], t.y, acc[i][j].y);
+            acc[i][j].z = fmaf(w[i], t.z, acc[i][j].z);
+            acc[i][j].w = fmaf(w[i], t.w, acc[i][j].w);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int sidx = s0 + warp * 4 + i;
+    if (sidx >= a.smax) continue;
+    float* dst = feat + (b * a.smax + sidx) * a.dim;
+#pragma unroll
+    for (int j = 0; j < kPoolMaxV4; ++j) {
+      const int c = lane + 32 * j;
+      if (c < dv4 && (acc[i][j].x != 0.f || acc[i][j].y != 0.f || acc[i][j].z != 0.f || acc[i][j].w != 0.f))
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * (c_base + c)), "f"(acc[i][j].x), "f"(acc[i][j].y),
+                     "f"(acc[i][j].z), "f"(acc[i][j].w)
+                     : "memory");
+    }
+  }
+}
+
+// Generic fallback of the pooling GEMM for feature widths that are not a multiple of 4 (the 90-d STEGO code):
+// scalar loads, 32 x 64 output block per CTA.
+// grid (ceil(dim/64), ceil(smax/32), B * ksplit); 256 threads: thread -> column tx, 8 rows.
+__global__ void __launch_bounds__(256)
+segment_pool_gemm_scalar_kernel(const float* __restrict__ wseg, const float* __restrict__ tok, float* __restrict__ feat,
                          SegmentArgs a, int ksplit) {
   __shared__ float Ws[32][33];
   __shared__ float Ts[32][64];
@@ -386,8 +469,23 @@ int segment_pool(const float* wseg, const float* tokens, const unsigned long lon
     WVN_CHECK_CUDA(cudaMemsetAsync(feat, 0, sizeof(float) * a.batch * a.smax * a.dim, stream));
     int ksplit = (P + 447) / 448;
     if (ksplit < 1) ksplit = 1;
-    dim3 grid((a.dim + 63) / 64, (a.smax + 31) / 32, a.batch * ksplit);
-    segment_pool_gemm_kernel<<<grid, 256, 0, stream>>>(wseg, tokens, feat, a, ksplit);
+    if (a.dim % 4 == 0) {
+      // 128 tokens per CTA: ~800 CTAs at 32 frames, 4 resident per SM, so one CTA's (unpipelined) tile load overlaps
+      // the others' FMAs; the extra partial sums are cheap vector atomics
+      ksplit = (P + 127) / 128;
+      const int col_blocks = (a.dim / 4 + 32 * kPoolMaxV4 - 1) / (32 * kPoolMaxV4);
+      dim3 grid(col_blocks, (a.smax + 31) / 32, a.batch * ksplit);
+      const size_t smem = (static_cast<size_t>(kPoolTok) * 32 * kPoolMaxV4 * 4 + 32 * (kPoolTok + 1)) * sizeof(float);
+      static bool attr_set = false;
+      if (!attr_set) {
+        WVN_CHECK_CUDA(cudaFuncSetAttribute(segment_pool_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+      }
+      segment_pool_gemm_kernel<<<grid, 256, smem, stream>>>(wseg, tokens, feat, a, ksplit);
+    } else {
+      dim3 grid((a.dim + 63) / 64, (a.smax + 31) / 32, a.batch * ksplit);
+      segment_pool_gemm_scalar_kernel<<<grid, 256, 0, stream>>>(wseg, tokens, feat, a, ksplit);
+    }
     WVN_CHECK_LAUNCH("segment_pool_gemm_kernel");
   }
   if (feat || centers) {
