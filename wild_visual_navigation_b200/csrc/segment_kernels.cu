@@ -79,8 +79,13 @@ segment_accumulate_kernel(const long long* __restrict__ seg, SegmentArgs a, unsi
 // of the token grid, so the bilinear weights W[s, token], the per-segment statistics and the
 // adjacency bits are first accumulated in shared memory (cheap, contention-free across SMs) and
 // only the non-zero entries are flushed with global atomics.  Used when smax <= kPrivMaxSeg.
-constexpr int kTileH = 8, kTileW = 64, kPrivMaxSeg = 128;
+constexpr int kTileH = 32, kTileW = 64, kPrivMaxSeg = 128;
+constexpr int kRun = 8;  // consecutive pixels of one row per thread: 256 threads = 32 rows x 8 runs
 
+// Each thread walks kRun consecutive pixels of one row and keeps the contribution of the current
+// (segment, token cell) run in registers; shared-memory atomics are issued once per run instead of seven per
+// pixel (neighbouring pixels almost always share segment and cell, so the per-pixel version serialised on
+// same-address atomics).
 __global__ void __launch_bounds__(256)
 segment_accumulate_tiled_kernel(const long long* __restrict__ seg, SegmentArgs a, int win_h, int win_w,
                                 unsigned long long* __restrict__ stats, float* __restrict__ wseg,
@@ -103,35 +108,57 @@ segment_accumulate_tiled_kernel(const long long* __restrict__ seg, SegmentArgs a
   ac_true_coord(px0, a.scale_x, a.grid_w, wx0, t1, tw);
   __syncthreads();
   const long long* segb = seg + b * a.h * a.w;
-  for (int i = threadIdx.x; i < kTileH * kTileW; i += blockDim.x) {
-    const int x = px0 + (i % kTileW), y = py0 + (i / kTileW);
-    if (x >= a.w || y >= a.h) continue;
-    const long long s = segb[static_cast<long long>(y) * a.w + x];
-    if (s < 0 || s >= a.smax) continue;
-    atomicAdd(&sm_stats[s * 3 + 0], 1);
-    atomicAdd(&sm_stats[s * 3 + 1], x);
-    atomicAdd(&sm_stats[s * 3 + 2], y);
-    if (wseg != nullptr) {
-      int x0, x1, y0, y1;
-      float wx, wy;
+  const int y = py0 + static_cast<int>(threadIdx.x) / (kTileW / kRun);
+  const int xs = px0 + (static_cast<int>(threadIdx.x) % (kTileW / kRun)) * kRun;
+  if (y < a.h && xs < a.w) {
+    const int n = min(kRun, a.w - xs);
+    long long ids[kRun + 1], below[kRun];
+    const long long* row = segb + static_cast<long long>(y) * a.w + xs;
+#pragma unroll
+    for (int i = 0; i <= kRun; ++i) ids[i] = (i < n || (i == n && xs + i < a.w)) ? row[i] : -1;  // ids[n] = right neighbour
+#pragma unroll
+    for (int i = 0; i < kRun; ++i) below[i] = (adj != nullptr && i < n && y + 1 < a.h) ? row[a.w + i] : -1;
+    int y0, y1;
+    float wy;
+    ac_true_coord(y, a.scale_y, a.grid_h, y0, y1, wy);
+    long long cur_s = -1;
+    int cur_x0 = -1, cur_x1 = -1, cnt = 0, sumx = 0;
+    float s_l = 0.f, s_r = 0.f;  // sums of (1 - wx) and wx over the run
+    auto flush = [&]() {
+      if (cur_s < 0) return;
+      atomicAdd(&sm_stats[cur_s * 3 + 0], cnt);
+      atomicAdd(&sm_stats[cur_s * 3 + 1], sumx);
+      atomicAdd(&sm_stats[cur_s * 3 + 2], cnt * y);
+      if (wseg != nullptr) {
+        float* w = sm_w + cur_s * win_h * win_w;
+        atomicAdd(w + (y0 - wy0) * win_w + (cur_x0 - wx0), (1.f - wy) * s_l);
+        atomicAdd(w + (y0 - wy0) * win_w + (cur_x1 - wx0), (1.f - wy) * s_r);
+        atomicAdd(w + (y1 - wy0) * win_w + (cur_x0 - wx0), wy * s_l);
+        atomicAdd(w + (y1 - wy0) * win_w + (cur_x1 - wx0), wy * s_r);
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < kRun; ++i) {
+      if (i >= n) break;
+      const long long sid = ids[i];
+      if (sid < 0 || sid >= a.smax) { flush(); cur_s = -1; continue; }
+      const int x = xs + i;
+      int x0, x1;
+      float wx;
       ac_true_coord(x, a.scale_x, a.grid_w, x0, x1, wx);
-      ac_true_coord(y, a.scale_y, a.grid_h, y0, y1, wy);
-      float* w = sm_w + s * win_h * win_w;
-      atomicAdd(w + (y0 - wy0) * win_w + (x0 - wx0), (1.f - wy) * (1.f - wx));
-      atomicAdd(w + (y0 - wy0) * win_w + (x1 - wx0), (1.f - wy) * wx);
-      atomicAdd(w + (y1 - wy0) * win_w + (x0 - wx0), wy * (1.f - wx));
-      atomicAdd(w + (y1 - wy0) * win_w + (x1 - wx0), wy * wx);
-    }
-    if (adj != nullptr) {
-      if (x + 1 < a.w) {
-        const long long r = segb[static_cast<long long>(y) * a.w + x + 1];
-        if (r != s && r >= 0 && r < a.smax) atomicOr(&sm_adj[r * adj_words + (s >> 5)], 1u << (s & 31));
+      if (sid != cur_s || x0 != cur_x0) {
+        flush();
+        cur_s = sid; cur_x0 = x0; cur_x1 = x1; cnt = 0; sumx = 0; s_l = 0.f; s_r = 0.f;
       }
-      if (y + 1 < a.h) {
-        const long long r = segb[static_cast<long long>(y + 1) * a.w + x];
-        if (r != s && r >= 0 && r < a.smax) atomicOr(&sm_adj[r * adj_words + (s >> 5)], 1u << (s & 31));
+      ++cnt; sumx += x; s_l += 1.f - wx; s_r += wx;
+      if (adj != nullptr) {
+        const long long r = ids[i + 1];
+        if (r != sid && r >= 0 && r < a.smax) atomicOr(&sm_adj[r * adj_words + (sid >> 5)], 1u << (sid & 31));
+        const long long d = below[i];
+        if (d != sid && d >= 0 && d < a.smax) atomicOr(&sm_adj[d * adj_words + (sid >> 5)], 1u << (sid & 31));
       }
     }
+    flush();
   }
   __syncthreads();
   for (int i = threadIdx.x; i < a.smax; i += blockDim.x) {
