@@ -1,13 +1,8 @@
 #!/bin/bash
-# iteration script (rewritten per experiment)
+# the round-end verification
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 600 python bench.py --steps 8 --warmup 3 --cpu-frames 0 2> gpurun_out/bench_iter.err | python -c "
-import sys, json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d = json.loads(l); r = d['roofline']
-        print('fps', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'attn TF', round(r['achieved'],1))
-"
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:segment_ -c 6 python bench.py --steps 1 --warmup 0 --profile-only 2>&1 | grep -E "segment_[a-z_]*kernel|gpu__time_duration" | sed 's/(const.*//' | head -12
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_default.json')); print('fps', d['value'], 'e2e', d['e2e']['value'], 'frac', d['roofline']['frac'], 'cpu', d['cpu_baseline']['value'])"
