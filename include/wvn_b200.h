@@ -158,6 +158,16 @@ int wvn_upsample_dense(const float* tokens, float* out, int batch, int dim, int 
 int wvn_logits_argmax(const float* logits, long long ld, int col0, int classes, int col0_b, int classes_b, int batch,
                       int npad, int gh, int gw, int out_h, int out_w, long long* seg, long long* seg_b, void* stream);
 
+/* Per-image k-means of the STEGO code (run_clustering=True — the reference's default for stego segmentation,
+ * feature_extractor.py:47-53; [EXTERNAL] Stego.postprocess(image_clustering=True), stego_interface.py:91-100).
+ * rows: the head-output matrix [batch*npad, ld] fp32 (row 0 of every frame = CLS), code in columns
+ * [code_col, code_col+code_dim).  Lloyd iterations (Euclidean, `iters` fixed, evenly spaced deterministic init) over the
+ * `patches` code rows of each frame; the per-patch nearest-centroid scores <x,c_k> - |c_k|^2/2 are written to columns
+ * [logit_col, logit_col+k) so that wvn_logits_argmax yields the per-pixel labels of the upsampled code.
+ * centroids_out: optional [batch, k, code_dim]. */
+int wvn_stego_kmeans(float* rows, long long ld, int batch, int npad, int patches, int code_col, int code_dim, int logit_col,
+                     int k, int iters, float* centroids_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Segment reductions — replace SegmentExtractor.adjacency_list / .centers
  * (feature_extractor/segment_extractor.py:40-92), FeatureExtractor.sparsify_features
@@ -241,6 +251,35 @@ int wvn_mlp_train_read_metrics(const void* scalars, float* metrics_out, void* st
 /* fp32 forward only: out [rows, 1+dim] (column 0 through the sigmoid), SimpleMLP.forward. */
 int wvn_mlp_forward_f32(int dim, int h1, int h2, const float* params, const float* x, int rows, float* h1_buf,
                         float* h2_buf, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused online train step — the same arithmetic as the three-phase entry points above in FOUR kernels, with the
+ * row compaction (`feat[seg_mask]`, wvn_feature_extractor_node.py:324-327 / nodes.py:199-241) and, for data-parallel
+ * runs, the two all-reduces inside the library (SURVEY.md §8b "wvn_mlp_train_step(..., ncclComm_t or NULL, ...)",
+ * §8e).  No host synchronisation, no allocation after create.
+ *   x: [groups, rows_per_group, dim] fp32, PADDED per group; n_rows: [groups] int32 (device) live rows per group, or
+ *   NULL when every row is live;  y [fp32] / y_valid [uint8] / confidence_out [fp32] are indexed by the COMPACTED row
+ *   number (live rows of group 0, then group 1, ...);  metrics_out (device, 6 floats, may be NULL): loss_total,
+ *   loss_trav, loss_reco, loss_trav_confidence, cg_mean, cg_std.  params / exp_avg / exp_avg_sq: flat fp32 buffers in
+ *   state_dict order (torch.optim.Adam state), step_counter: device int64.
+ * phase_mask: 7 = whole step; 1 / 2 / 4 = forward+stats / backward+weight-gradients / metrics+Adam separately (a caller
+ * without a library communicator all-reduces `scalars` (6 doubles) after phase 1 and `grads` (n_params + 1) after 2).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct wvn_mlp_trainer wvn_mlp_trainer_t;
+/* scalars: optional caller-owned device buffer of wvn_mlp_trainer_scalars_bytes(); grads: optional caller-owned device
+ * buffer of n_params + 1 floats (NULL: the trainer allocates them with its workspace). */
+size_t wvn_mlp_trainer_scalars_bytes(void);
+int wvn_mlp_trainer_create(int dim, int h1, int h2, int max_rows, const wvn_train_config* cfg, void* scalars,
+                           float* grads, wvn_mlp_trainer_t** out);
+void wvn_mlp_trainer_destroy(wvn_mlp_trainer_t* t);
+/* Library-owned NCCL communicator (libnccl.so.2 is resolved from the running process): rank 0 fills a 128-byte id with
+ * wvn_comm_unique_id, the caller broadcasts it by any means, every rank calls wvn_mlp_trainer_init_comm. */
+int wvn_comm_unique_id(void* id128);
+int wvn_mlp_trainer_init_comm(wvn_mlp_trainer_t* t, const void* id128, int rank, int world);
+int wvn_mlp_train_step(wvn_mlp_trainer_t* t, float* params, float* exp_avg, float* exp_avg_sq, long long* step_counter,
+                       const float* x, int groups, int rows_per_group, const int* n_rows, const float* y,
+                       const unsigned char* y_valid, float* cg_mean, float* cg_std, float* confidence_out,
+                       float* metrics_out, int phase_mask, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,17 +18,19 @@ from .dino_vit import ViTConfig, vit_feature_map
 
 
 @torch.no_grad()
-def frame_features(img: torch.Tensor, sd: dict, cfg: ViTConfig, hd: dict | None, flip_tta: bool = False):
+def frame_features(img: torch.Tensor, sd: dict, cfg: ViTConfig, hd: dict | None, flip_tta: bool = False,
+                   n_image_clusters: int = 0, kmeans_iters: int = 10):
     """img (1,3,H,W).  Returns dict(dense (1,D,H,H), seg (H,H) long | None, feat (S,D) | None,
     edges, centers)."""
     timg = wvn_path.wvn_transform(img, cfg.image_size)
     fmap = vit_feature_map(timg, sd, cfg)
     H = img.shape[2]
     dense = F.interpolate(fmap, (H, H), mode="bilinear", align_corners=True)
-    out = {"dense": dense, "seg": None, "feat": None, "edges": None, "centers": None}
+    out = {"dense": dense, "fmap": fmap, "seg": None, "feat": None, "edges": None, "centers": None}
     if hd is not None:
         fmap_f = vit_feature_map(timg.flip(dims=[3]), sd, cfg) if flip_tta else None
-        _, cluster, _ = stego_head.stego_inference(fmap, fmap_f, hd, (cfg.image_size, cfg.image_size))
+        _, cluster, _ = stego_head.stego_inference(fmap, fmap_f, hd, (cfg.image_size, cfg.image_size),
+                                                   n_image_clusters=n_image_clusters, kmeans_iters=kmeans_iters)
         seg = wvn_path.relabel(cluster[0].long())
         out["seg"] = seg
         out["edges"] = wvn_path.adjacency_list(seg[None, None])
@@ -38,12 +40,13 @@ def frame_features(img: torch.Tensor, sd: dict, cfg: ViTConfig, hd: dict | None,
 
 
 def cpu_step(imgs: torch.Tensor, sd: dict, cfg: ViTConfig, hd: dict, mlp_sd: dict, opt_state, cg_mean, cg_std,
-             std_factor: float = 0.5, supervision_seed: int = 2, flip_tta: bool = False, train: bool = True):
+             std_factor: float = 0.5, supervision_seed: int = 2, flip_tta: bool = False, train: bool = True,
+             n_image_clusters: int = 0, kmeans_iters: int = 10):
     """Full step over a batch of frames (frame by frame, as the reference's B=1 contract demands).
     Returns (trav [B,H,H], conf [B,H,H], new_mlp_sd, new_opt_state, metrics)."""
     travs, confs, rows = [], [], []
     for b in range(imgs.shape[0]):
-        f = frame_features(imgs[b : b + 1], sd, cfg, hd, flip_tta)
+        f = frame_features(imgs[b : b + 1], sd, cfg, hd, flip_tta, n_image_clusters, kmeans_iters)
         t, c = wvn_path.pixel_inference(f["dense"], mlp_sd, cg_mean, cg_std, std_factor)
         travs.append(t)
         confs.append(c)

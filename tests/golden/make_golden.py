@@ -14,6 +14,7 @@ Fixtures
   supervision.pt    MissionNode.update_supervision_signal (the reference's method source, executed from the reference file)
   sparsify.pt       FeatureExtractor.sparsify_features (loop + cumsum variants) and segment_stego's relabel loop,
                     the reference's method sources executed from the reference file
+  checkpoint_ref.pt a checkpoint as TraversabilityEstimator.save_checkpoint writes it, from the reference's classes
   tmp_state_dict.pt the weight hand-off file as wvn_learning_node.py:381-394 writes it (reference SimpleMLP + ConfidenceGenerator)
   segments.npz      reference SegmentExtractor on a synthetic map + the reference's shipped
                     known-answer assets/graph/{seg,center}.pt and graph.pt edge_index
@@ -114,6 +115,34 @@ def make_handoff(ns):
     new_model_state_dict = model.state_dict()
     new_model_state_dict["confidence_generator"] = cg.get_dict()
     torch.save(new_model_state_dict, os.path.join(HERE, "tmp_state_dict.pt"))
+
+
+def make_checkpoint(ns):
+    """last_checkpoint.pt exactly as TraversabilityEstimator.save_checkpoint writes it
+    (traversability_estimator.py:377-399: step / model_state_dict / optimizer_state_dict /
+    traversability_loss_state_dict / loss) from the reference's own SimpleMLP, TraversabilityLoss (which registers the
+    model as a sub-module: its state dict carries ``_model.layers.*``) and torch.optim.Adam after two steps."""
+    torch.manual_seed(42)
+    model = ns.SimpleMLP(16, [8, 4, 1], True)   # small dims: the FORMAT is what this fixture pins
+    loss_fn = ns.TraversabilityLoss(w_trav=0.03, w_reco=0.5, w_temp=0.0, anomaly_balanced=True, model=model,
+                                    method="latest_measurement", confidence_std_factor=0.5, log_enabled=False,
+                                    log_folder="/tmp")
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(48, 16, generator=g)
+    yv = torch.rand(48, generator=g) < 0.3
+    y = torch.where(yv, torch.rand(48, generator=g).clamp(min=0.001), torch.zeros(48))
+    loss = None
+    for step in range(2):
+        graph = ns.Data(x=x, y=y, y_valid=yv)
+        loss, _, _ = loss_fn(graph, model(graph), step=step, log_step=False)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    torch.save({"step": 2, "model_state_dict": model.state_dict(), "optimizer_state_dict": opt.state_dict(),
+                "traversability_loss_state_dict": loss_fn.state_dict(), "loss": loss.item()},
+               os.path.join(HERE, "checkpoint_ref.pt"))
+    torch.save({"x": x, "y": y, "y_valid": yv}, os.path.join(HERE, "checkpoint_ref_batch.pt"))
 
 
 def make_supervision():
@@ -379,6 +408,7 @@ if __name__ == "__main__":
     make_mlp_init(ns)
     make_confidence(ns)
     make_handoff(ns)
+    make_checkpoint(ns)
     make_supervision()
     make_sparsify()
     make_segments(ns)

@@ -76,6 +76,24 @@ def test_simple_mlp_state_dict_layout_and_quirk():
     assert m2.output_features == 91
 
 
+def test_checkpoint_keys_match_reference_made_checkpoint(golden_dir):
+    """A checkpoint written by the reference's own classes (tests/golden/checkpoint_ref.pt, make_golden.py) and the
+    state dicts this package produces have the same keys — in both directions strict load_state_dict works."""
+    from wild_visual_navigation_b200 import SimpleMLP, TraversabilityLoss
+
+    ck = torch.load(os.path.join(golden_dir, "checkpoint_ref.pt"), weights_only=False)
+    assert set(ck) == {"step", "model_state_dict", "optimizer_state_dict", "traversability_loss_state_dict", "loss"}
+    model = SimpleMLP(16, [8, 4, 1], True)
+    loss = TraversabilityLoss(0.03, 0.5, 0.0, True, model, "latest_measurement", 0.5)
+    assert list(model.state_dict()) == list(ck["model_state_dict"])
+    assert list(loss.state_dict()) == list(ck["traversability_loss_state_dict"])
+    model.load_state_dict(ck["model_state_dict"])                      # strict
+    loss.load_state_dict(ck["traversability_loss_state_dict"])         # strict: needs the _model.* keys
+    assert torch.equal(model.flat_params[: 8 * 16].view(8, 16), ck["model_state_dict"]["layers.0.weight"])
+    assert torch.equal(loss._confidence_generator.mean, ck["traversability_loss_state_dict"]["_confidence_generator.mean"])
+    assert len(ck["optimizer_state_dict"]["state"]) == 6 and "exp_avg" in ck["optimizer_state_dict"]["state"][0]
+
+
 def test_confidence_generator_state_dict_keys():
     from wild_visual_navigation_b200 import ConfidenceGenerator, TraversabilityLoss, SimpleMLP
 
@@ -83,6 +101,10 @@ def test_confidence_generator_state_dict_keys():
     assert set(cg.state_dict()) == {"mean", "var", "std"}
     assert cg.var.shape == (1, 1)
     loss = TraversabilityLoss(0.03, 0.5, 0.0, True, SimpleMLP(8, [4, 2, 1], True), "latest_measurement", 0.5)
-    assert set(loss.state_dict()) == {"_confidence_generator.mean", "_confidence_generator.var", "_confidence_generator.std"}
+    # the reference registers the model as a sub-module of the loss (loss.py:74), so its keys ride in this state dict
+    assert list(loss.state_dict()) == ["_model.layers.0.weight", "_model.layers.0.bias", "_model.layers.2.weight",
+                                       "_model.layers.2.bias", "_model.layers.4.weight", "_model.layers.4.bias",
+                                       "_confidence_generator.mean", "_confidence_generator.var",
+                                       "_confidence_generator.std"]
     x = torch.rand(10)
     assert torch.equal(cg.inference_without_update(x.to("meta")) if False else cg.inference_without_update(x), cg.inference_without_update(x))

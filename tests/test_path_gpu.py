@@ -230,7 +230,7 @@ def test_feature_extractor_extract_contract_vs_oracle(golden_dir):
     sd = synthetic_state_dict(cfg, seed=6)
     hd = stego_head.synthetic_head(384, 90, 32, 27, seed=3)
     fe = FeatureExtractor("cuda", segmentation_type="stego", feature_type="stego", input_size=224, state_dict=sd,
-                          head_state_dict=hd, flip_tta=True, max_batch=2)
+                          head_state_dict=hd, flip_tta=True, run_clustering=False, max_batch=2)
     img = torch.rand(1, 3, 224, 224, generator=torch.Generator().manual_seed(8)).cuda()
     edges, feat, seg, center, dense = fe.extract(img, return_dense_features=True)
     assert fe.feature_dim == 90 and fe.feature_type == "stego" and fe.segmentation_type == "stego"
@@ -250,6 +250,54 @@ def test_feature_extractor_extract_contract_vs_oracle(golden_dir):
     assert (feat - feat_ref).abs().max() <= 2e-3 * feat_ref.abs().max()
     assert (center - wvn_path.centers(seg[None, None])).abs().max() < 1e-3
     assert torch.equal(edges, wvn_path.adjacency_list(seg[None, None]).T)
+
+
+@pytest.mark.parametrize("flip_tta", [False, True])
+def test_stego_per_image_kmeans_default(flip_tta):
+    """run_clustering=True / n_image_clusters=20 — what WVN actually runs for stego segmentation
+    (feature_extractor.py:47-53; the ROS node does not override it): the cluster segments come from the per-image
+    k-means of the code (csrc/stego_kmeans.cu) and must agree with the oracle's restatement (oracle/stego_head.py:
+    image_kmeans + kmeans_predict, fixed init / iteration count) on >= 98 % of the pixels; the centroids themselves to
+    1e-3 relative when both sides start from the SAME code (fp32 both sides: only summation order differs)."""
+    from oracle import stego_head, wvn_path
+    from oracle.dino_vit import ViTConfig, synthetic_state_dict, vit_feature_map
+    from wild_visual_navigation_b200 import ops
+    from wild_visual_navigation_b200.feature_extractor import FeatureExtractor
+    from wild_visual_navigation_b200.feature_extractor.weights import HEAD_CLUSTER_COL, HEAD_CODE_COL
+
+    cfg = ViTConfig.from_name("vit_small", 8, 224)
+    sd = synthetic_state_dict(cfg, seed=6)
+    hd = stego_head.synthetic_head(384, 90, 32, 27, seed=3)
+    fe = FeatureExtractor("cuda", segmentation_type="stego", feature_type="stego", input_size=224, state_dict=sd,
+                          head_state_dict=hd, flip_tta=flip_tta, max_batch=2)           # defaults: run_clustering=True, K=20
+    assert fe._stego._cfg.run_clustering and fe.max_segments == 20
+    img = torch.rand(2, 3, 224, 224, generator=torch.Generator().manual_seed(8)).cuda()
+    r = fe.extract_batch(img)
+    sdc, hdc = _to(sd, "cuda"), _to(hd, "cuda")
+    t = wvn_path.wvn_transform(img, 224)
+    f = vit_feature_map(t, sdc, cfg)
+    ff = vit_feature_map(t.flip(dims=[3]), sdc, cfg) if flip_tta else None
+    _, cluster, _ = stego_head.stego_inference(f, ff, hdc, (224, 224), n_image_clusters=20, kmeans_iters=10)
+    for b in range(2):
+        seg_ref = wvn_path.relabel(cluster[b].long())
+        agree = (r["seg"][b] == seg_ref).float().mean().item()
+        print(f"k-means segments (flip_tta={flip_tta}) frame {b}: agreement {agree:.4f}, segments {int(r['n_segments'][b])}")
+        assert agree >= 0.98
+        assert int(r["n_segments"][b]) == int(seg_ref.max()) + 1 <= 20
+    # kernel vs oracle on IDENTICAL code: centroids and per-patch scores
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, P, npad, ld, K = 3, 28 * 28, 896, 256, 20
+    rows = torch.zeros(B * npad, ld, device="cuda")
+    code = torch.randn(B, P, 90, device="cuda", generator=g) + 2.0 * torch.randn(B, 1, 90, device="cuda", generator=g)
+    rows.view(B, npad, ld)[:, 1 : 1 + P, HEAD_CODE_COL : HEAD_CODE_COL + 90] = code
+    cent = torch.empty(B, K, 90, device="cuda")
+    ops.check(ops.lib().wvn_stego_kmeans(ops.ptr(rows), ld, B, npad, P, HEAD_CODE_COL, 90, HEAD_CLUSTER_COL, K, 10,
+                                         ops.ptr(cent), ops.stream()))
+    cent_ref = stego_head.image_kmeans(code.transpose(1, 2).reshape(B, 90, 28, 28), K, 10)
+    assert rel_l2(cent, cent_ref) <= 1e-3, rel_l2(cent, cent_ref)
+    score = rows.view(B, npad, ld)[:, 1 : 1 + P, HEAD_CLUSTER_COL : HEAD_CLUSTER_COL + K]
+    score_ref = code @ cent_ref.transpose(1, 2) - 0.5 * (cent_ref**2).sum(-1)[:, None, :]
+    assert (score - score_ref).abs().max() <= 1e-2 * score_ref.abs().max()
 
 
 def test_segment_known_answer_asset(golden_dir):

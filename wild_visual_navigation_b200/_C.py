@@ -58,6 +58,7 @@ SIGNATURES = {
     "wvn_vit_npad": (_I, [_P]),
     "wvn_upsample_dense": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "wvn_logits_argmax": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "wvn_stego_kmeans": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "wvn_segment_workspace_bytes": (_S, [_I, _I, _I, _I]),
     "wvn_segment_reduce": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
     "wvn_segment_relabel": (_I, [_P, _I, _L, _I, _P, _P, _P]),
@@ -75,6 +76,12 @@ SIGNATURES = {
     "wvn_mlp_train_apply": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _L, POINTER(TrainConfig), _P, _P]),
     "wvn_mlp_train_read_metrics": (_I, [_P, _P, _P]),
     "wvn_mlp_forward_f32": (_I, [_I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
+    "wvn_mlp_trainer_scalars_bytes": (_S, []),
+    "wvn_mlp_trainer_create": (_I, [_I, _I, _I, _I, POINTER(TrainConfig), _P, _P, POINTER(_P)]),
+    "wvn_mlp_trainer_destroy": (None, [_P]),
+    "wvn_comm_unique_id": (_I, [_P]),
+    "wvn_mlp_trainer_init_comm": (_I, [_P, _P, _I, _I]),
+    "wvn_mlp_train_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
 }
 
 

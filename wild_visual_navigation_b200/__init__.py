@@ -20,3 +20,4 @@ from .feature_extractor import (  # noqa: E402,F401
 )
 from .traversability_estimator import TraversabilityEstimator  # noqa: E402,F401
 from .inference import TraversabilityInference  # noqa: E402,F401
+from .hot_path import HotPathStep  # noqa: E402,F401

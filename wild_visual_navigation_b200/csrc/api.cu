@@ -14,8 +14,10 @@
 #include "gemm.h"
 #include "host_common.h"
 #include "mlp_train.h"
+#include "mlp_train_fused.h"
 #include "pixel_head.h"
 #include "segment_kernels.h"
+#include "stego_kmeans.h"
 #include "vit_kernels.h"
 
 using namespace wvn;
@@ -178,10 +180,17 @@ int wvn_attention_bf16(const void* q, const void* k, const void* vt, void* out, 
   if (timing_on && rc == 0) {
     cudaStreamSynchronize(S(stream));
     const int nkv = npad / 128;
-    fprintf(stderr, "[attn timing, cycles per KV tile] softmax: wait_s %lld  ldtm %lld  math %lld  wait_pv %lld  store+fence %lld | "
-            "mma: issue_qk(+waits) %lld  wait_p %lld  wait_v+issue_pv %lld  loop %lld\n",
-            timing_buf[0] / nkv, timing_buf[1] / nkv, timing_buf[2] / nkv, timing_buf[3] / nkv, timing_buf[4] / nkv,
-            timing_buf[8] / nkv, timing_buf[9] / nkv, timing_buf[10] / nkv, timing_buf[11] / nkv);
+    const char* impl = getenv("WVN_ATTN_IMPL");
+    if (impl && atoi(impl) == 1)
+      fprintf(stderr, "[attn v1 timing, cycles per KV tile] softmax: wait_s %lld  ldtm %lld  math %lld  wait_pv %lld  store+fence %lld | "
+              "mma: issue_qk(+waits) %lld  wait_p %lld  wait_v+issue_pv %lld  loop %lld\n",
+              timing_buf[0] / nkv, timing_buf[1] / nkv, timing_buf[2] / nkv, timing_buf[3] / nkv, timing_buf[4] / nkv,
+              timing_buf[8] / nkv, timing_buf[9] / nkv, timing_buf[10] / nkv, timing_buf[11] / nkv);
+    else
+      fprintf(stderr, "[attn v2 timing, cycles per KV tile] softmax wg0: wait_s %lld  ldtm %lld  max+rescale %lld  token_wait %lld  exp %lld  "
+              "wait_pv+store %lld | mma: wait_v+wait_p0 %lld  pv0+wait_sfree0+qk0 %lld  wait_p1 %lld  pv1+qk1+loop %lld\n",
+              timing_buf[0] / nkv, timing_buf[1] / nkv, timing_buf[2] / nkv, timing_buf[5] / nkv, timing_buf[3] / nkv,
+              timing_buf[4] / nkv, timing_buf[8] / nkv, timing_buf[9] / nkv, timing_buf[10] / nkv, timing_buf[11] / nkv);
   }
   return rc;
 }
@@ -516,6 +525,14 @@ int wvn_logits_argmax(const float* logits, long long ld, int col0, int classes, 
   return logits_argmax(logits, seg, seg_b, a, S(stream));
 }
 
+int wvn_stego_kmeans(float* rows, long long ld, int batch, int npad, int patches, int code_col, int code_dim, int logit_col,
+                     int k, int iters, float* centroids_out, void* stream) {
+  KmeansArgs a;
+  a.batch = batch; a.npad = npad; a.patches = patches; a.ld = ld; a.code_col = code_col; a.code_dim = code_dim;
+  a.logit_col = logit_col; a.k = k; a.iters = iters; a.centroids_out = centroids_out;
+  return stego_kmeans(rows, a, S(stream));
+}
+
 // -------------------------------------------------------------------------------- segments
 static void seg_ws_layout(int batch, int smax, int gh, int gw, size_t& off_w, size_t& off_adj, size_t& total) {
   const size_t stats = static_cast<size_t>(batch) * smax * 3 * sizeof(unsigned long long);
@@ -537,6 +554,9 @@ int wvn_segment_reduce(const long long* seg, int batch, int h, int w, int smax, 
   WVN_REQUIRE(seg && workspace, "wvn_segment_reduce: null argument");
   WVN_REQUIRE(feat == nullptr || tokens != nullptr, "wvn_segment_reduce: feat requested without tokens");
   WVN_REQUIRE((edges == nullptr) == (n_edges == nullptr), "wvn_segment_reduce: edges and n_edges go together");
+  // dense features exist on (h, h) only (dino_interface.py:87-88): pixels with x >= h have no feature — the reference
+  // raises an index error there, so do we
+  WVN_REQUIRE(feat == nullptr || w <= h, "wvn_segment_reduce: segment map %dx%d is wider than the (h, h) feature map", h, w);
   size_t off_w, off_adj, total;
   seg_ws_layout(batch, smax, gh, gw, off_w, off_adj, total);
   char* ws = reinterpret_cast<char*>(workspace);
@@ -878,6 +898,50 @@ int wvn_mlp_forward_f32(int dim, int h1, int h2, const float* params, const floa
                         float* h2_buf, float* out, void* stream) {
   WVN_REQUIRE(params && x && h1_buf && h2_buf && out && rows > 0, "wvn_mlp_forward_f32: bad argument");
   return mlp_forward_f32(shape_of(dim, h1, h2), params, x, rows, h1_buf, h2_buf, out, S(stream));
+}
+
+
+// -------------------------------------------------------------------------------- fused train step
+struct wvn_mlp_trainer {
+  FusedTrainer* impl = nullptr;
+};
+
+size_t wvn_mlp_trainer_scalars_bytes(void) { return sizeof(FusedScalars); }
+
+int wvn_mlp_trainer_create(int dim, int h1, int h2, int max_rows, const wvn_train_config* cfg, void* scalars, float* grads,
+                           wvn_mlp_trainer_t** out) {
+  WVN_REQUIRE(cfg && out, "wvn_mlp_trainer_create: null argument");
+  WVN_PROPAGATE(wvn_check_device());
+  AdamCfg a;
+  a.lr = cfg->lr; a.beta1 = cfg->beta1; a.beta2 = cfg->beta2; a.eps = cfg->eps;
+  FusedTrainer* impl = nullptr;
+  WVN_PROPAGATE(fused_trainer_create(shape_of(dim, h1, h2), max_rows, loss_of(cfg), a, scalars, grads, &impl));
+  wvn_mlp_trainer* t = new wvn_mlp_trainer();
+  t->impl = impl;
+  *out = t;
+  return WVN_OK;
+}
+
+void wvn_mlp_trainer_destroy(wvn_mlp_trainer_t* t) {
+  if (!t) return;
+  fused_trainer_destroy(t->impl);
+  delete t;
+}
+
+int wvn_comm_unique_id(void* id128) { return fused_comm_unique_id(id128); }
+
+int wvn_mlp_trainer_init_comm(wvn_mlp_trainer_t* t, const void* id128, int rank, int world) {
+  WVN_REQUIRE(t, "wvn_mlp_trainer_init_comm: null trainer");
+  return fused_trainer_init_comm(t->impl, id128, rank, world);
+}
+
+int wvn_mlp_train_step(wvn_mlp_trainer_t* t, float* params, float* exp_avg, float* exp_avg_sq, long long* step_counter,
+                       const float* x, int groups, int rows_per_group, const int* n_rows, const float* y,
+                       const unsigned char* y_valid, float* cg_mean, float* cg_std, float* confidence_out,
+                       float* metrics_out, int phase_mask, void* stream) {
+  WVN_REQUIRE(t, "wvn_mlp_train_step: null trainer");
+  return fused_train_step(t->impl, params, exp_avg, exp_avg_sq, step_counter, x, groups, rows_per_group, n_rows, y, y_valid,
+                          cg_mean, cg_std, confidence_out, metrics_out, phase_mask, S(stream));
 }
 
 }  // extern "C"

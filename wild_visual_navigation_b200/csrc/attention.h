@@ -13,6 +13,7 @@ struct AttnArgs {
   void* out = nullptr;     // [batch, npad, ldo] bf16, head h occupies columns [64h, 64h+64)
   long long ldo = 0;
   int reverse = 0;     // walk (frame, head, q-tile) last-to-first: start on what the QKV GEMM wrote last (L2 hits)
+  int no_token = 0;    // debug: v2 kernel without the exp-phase ordering between its two softmax warpgroups
   long long* timing = nullptr;  // debug: 16 cycle counters of block (0,0) (see scripts/bench_attention.py)
 };
 

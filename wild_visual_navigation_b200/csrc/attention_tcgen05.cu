@@ -51,6 +51,16 @@ constexpr uint32_t kTmemCols = 256;  // S: [0,128)  O: [128,192)  P (bf16 pairs)
 constexpr uint32_t kColS = 0;
 constexpr uint32_t kColO = 128;
 constexpr uint32_t kColP = 192;
+// Warp roles.  The sub-partition arbiter prefers the HIGHEST warp id among eligible warps (B300 microarchitecture notes,
+// measured): with the single-thread producer / MMA-issuer warps at ids 0 / 1 the MMA issuer lost every arbitration
+// against the two busy softmax warps of its sub-partition and needed ~700 clk to issue 8 UMMAs + 2 commits (round 2
+// phase timing) — the whole pipeline then waits on it.  $WVN_ATTN_AUX_FIRST=1 at compile time restores the old layout.
+#ifdef WVN_ATTN_AUX_FIRST
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpSoftmax0 = 2;
+#else
+constexpr int kWarpSoftmax0 = 0, kWarpTma = 4, kWarpMma = 5;
+#endif
+constexpr int kTimingThread = kWarpSoftmax0 * 32;
 constexpr float kRescaleThreshold = 8.0f;  // in log2 units (FA4-style lazy rescale)
 constexpr int kDefaultPoly = 2;            // software-exp2 share: pairs out of every 8 pairs (see poly_exp2_pair)
 
@@ -245,7 +255,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     printf("[wvn] attention: dynamic smem base not 1024B aligned\n");
     __trap();
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kWarpMma && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
@@ -259,13 +269,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == kWarpTma) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kWarpTma) {
     // -------------------------------------------------------------- TMA producer
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q);
@@ -286,7 +296,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tma_load_2d(&tmap_vt, &v_full[st], smem + kOffV + st * kVBytes + kVBytes / 2, j * kTileKV + 64, bh * kDh);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV);  // 128 x 128
@@ -361,7 +371,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     c.l = 0.f;            // running sum of exp2((s - m_ref) * sl2)
     // optional phase timing (debug): cycles spent by this thread in each phase, summed over tiles
 #ifdef WVN_ATTN_TIMING
-    const bool timing = args.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
+    const bool timing = args.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == kTimingThread;
     long long tph[5] = {0, 0, 0, 0, 0}, tprev = timing ? clock64() : 0;
 #else
     constexpr bool timing = false;
@@ -401,9 +411,421 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == kWarpTma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+
+// =====================================================================================================================
+// v2 (round 2): ONE CTA per SM owns TWO 128-row query tiles of one (frame, head).
+//
+// What round 1's ncu source page showed for the kernel above (2 independent CTAs per SM): the exponentials of the two
+// co-resident CTAs run in lock-step — both softmax warps of an SM sub-partition sit in their MUFU phase together
+// (sharing the 4 ex2/clk of that sub-partition) and then both leave the XU pipe idle while they load S / take the row
+// max / hand P over — XU 52 % active, tensor 34 %; and 30 % of all issued instructions were the wait loops of the two
+// single-thread warps.  Here the two query tiles belong to one CTA, so their softmax warpgroups can be ORDERED:
+//   warp 0     : TMA producer (Q0, Q1 once; K / V^T tiles in a 3-stage ring shared by both query tiles)
+//   warp 1     : MMA issuer for both tiles, in the order the anti-phased warpgroups need the results
+//                (PV0(j), QK0(j+2), PV1(j), QK1(j+2): S of a tile is always computed one full period ahead)
+//   warps 2-3  : idle (they complete the first warpgroup, which gives its registers away with setmaxnreg.dec)
+//   warps 4-7  : softmax warpgroup 0 (query tile 0), 1 thread = 1 row, 232 registers (setmaxnreg.inc): no spills
+//   warps 8-11 : softmax warpgroup 1 (query tile 1)
+// The exp2 phase is a token passed between the warpgroups through two named barriers: while one warpgroup owns the XU
+// pipe, the other does its MUFU-free work (P -> TMEM, wait S, tcgen05.ld, row max), so each sub-partition always has
+// exactly one warp issuing MUFU — the pipe the kernel is bound by (16 ex2/clk/SM vs 2 x 128 x 128 exps per KV step).
+// Tensor memory: 2 x (S 128 | O 64 | P 64) = all 512 columns.  K / V^T are fetched once per PAIR of query tiles.
+// =====================================================================================================================
+namespace v2 {
+constexpr int kThreads = 384;  // warps 0-3: producer, MMA issuer, 2 idle (one warpgroup, so setmaxnreg can shrink it); 4-11: softmax
+constexpr int kRegsAux = 56, kRegsSoftmax = 224;  // per SM sub-partition: 56 + 2 * 224 = 3 * 168 (the launch allocation)
+constexpr int kStages = 3;
+constexpr uint32_t kOffQ = 0;  // Q0 | Q1
+constexpr uint32_t kOffK = kOffQ + 2 * kQBytes;
+constexpr uint32_t kOffV = kOffK + kStages * kKBytes;
+constexpr uint32_t kOffBar = kOffV + kStages * kVBytes;
+constexpr uint32_t kSmemBytes = kOffBar + 256;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTileCols = 256;  // per query tile: S [0,128)  O [128,192)  P [192,256)
+constexpr int kBarWg0 = 1, kBarWg1 = 2;  // named barriers: "warpgroup 0 / 1 may start its exp phase"
+#ifdef WVN_ATTN_AUX_FIRST
+constexpr int kWarpAux0 = 0, kWarpTma = 0, kWarpMma = 1, kWarpSoftmax0 = 4;   // aux warpgroup = warps 0-3
+#else
+constexpr int kWarpSoftmax0 = 0, kWarpAux0 = 8, kWarpTma = 8, kWarpMma = 9;   // aux warpgroup = warps 8-11
+#endif
+}  // namespace v2
+
+struct SoftmaxCtx2 {
+  uint32_t tmem_s, tmem_o, tmem_p;
+  float sl2;
+  uint64_t *s_full, *s_free, *p_full, *pv_done;
+  float m_ref, l;
+  int wg, nkv;
+  bool paired;  // the other warpgroup is active: exp phases alternate
+};
+
+template <int POLY, bool MASKED>
+__device__ __forceinline__ void softmax_tile2(SoftmaxCtx2& c, int j, int valid, long long* tph, bool timing,
+                                              long long& tprev) {
+#ifdef WVN_ATTN_TIMING
+#define WVN_TPH(i) if (timing) { const long long tn = clock64(); tph[i] += tn - tprev; tprev = tn; }
+#else
+#define WVN_TPH(i)
+#endif
+  mbar_wait(c.s_full, j & 1);
+  tc_fence_after();
+  WVN_TPH(0)
+  uint32_t sr[4][32];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tmem_ld32(c.tmem_s + q * 32, sr[q]);
+  tmem_ld_wait();
+  tc_fence_before();
+  mbar_arrive(c.s_free);  // S(j) is in registers: QK^T(j+2) may overwrite it
+  WVN_TPH(1)
+
+  float mx;
+  if (!MASKED) {
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // FMNMX3 chains
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      m0 = max3(m0, __uint_as_float(sr[0][i]), __uint_as_float(sr[0][i + 1]));
+      m1 = max3(m1, __uint_as_float(sr[1][i]), __uint_as_float(sr[1][i + 1]));
+      m2 = max3(m2, __uint_as_float(sr[2][i]), __uint_as_float(sr[2][i + 1]));
+      m3 = max3(m3, __uint_as_float(sr[3][i]), __uint_as_float(sr[3][i + 1]));
+    }
+    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  } else {
+    mx = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (q * 32 + i < valid) ? __uint_as_float(sr[q][i]) : -INFINITY);
+  }
+
+  // ---- reference-max update (lazy: only rescale O when the max grew by > 2^8)
+  bool waited_pv = false;
+  if (j == 0) {
+    c.m_ref = mx;
+  } else {
+    const float m_new = fmaxf(c.m_ref, mx);
+    const bool need = (m_new - c.m_ref) * c.sl2 > kRescaleThreshold;
+    if (__any_sync(0xffffffffu, need)) {
+      mbar_wait(c.pv_done, (j - 1) & 1);  // O must be quiescent
+      waited_pv = true;
+      tc_fence_after();
+      const float alpha = need ? fast_exp2((c.m_ref - m_new) * c.sl2) : 1.f;
+      if (need) c.m_ref = m_new;
+      c.l *= alpha;
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        uint32_t r[32];
+        tmem_ld32(c.tmem_o + q * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+        tmem_st32(c.tmem_o + q * 32, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+    }
+  }
+  WVN_TPH(2)
+
+  // ---- exp phase: owned by one warpgroup at a time
+  if (c.paired && (c.wg == 1 || j > 0)) named_bar_sync(c.wg ? v2::kBarWg1 : v2::kBarWg0, 256);
+  WVN_TPH(5)
+  const float mb = c.m_ref * c.sl2;
+  if (!MASKED) {
+    const uint64_t sl2_2 = pack2(c.sl2, c.sl2), nmb2 = pack2(-mb, -mb);
+    uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f), lc = pack2(0.f, 0.f), ld = pack2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const uint64_t x2 = fma2(pack2(__uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1])), sl2_2, nmb2);
+        float e0, e1;
+        if (POLY == 9) {  // timing experiment only: no exponentials at all (results are wrong)
+          unpack2(x2, e0, e1);
+        } else if (((i >> 1) & 7) < POLY) {
+          poly_exp2_pair(x2, e0, e1);
+        } else {
+          float x0, x1;
+          unpack2(x2, x0, x1);
+          e0 = fast_exp2(x0);
+          e1 = fast_exp2(x1);
+        }
+        const uint64_t e2 = pack2(e0, e1);
+        switch ((i >> 1) & 3) {
+          case 0: la = add2(la, e2); break;
+          case 1: lb = add2(lb, e2); break;
+          case 2: lc = add2(lc, e2); break;
+          default: ld = add2(ld, e2); break;
+        }
+        sr[q >> 1][(q & 1) * 16 + (i >> 1)] = pack_bf16x2(e0, e1);  // packed pairs overwrite consumed scores: P columns [0,64)
+      }
+    }
+    float s0, s1;
+    unpack2(add2(add2(la, lb), add2(lc, ld)), s0, s1);
+    c.l += s0 + s1;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const int col = q * 32 + i;
+        const float e0 = (col < valid) ? fast_exp2(fmaf(__uint_as_float(sr[q][i]), c.sl2, -mb)) : 0.f;
+        const float e1 = (col + 1 < valid) ? fast_exp2(fmaf(__uint_as_float(sr[q][i + 1]), c.sl2, -mb)) : 0.f;
+        c.l += e0 + e1;
+        sr[q >> 1][(q & 1) * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
+      }
+    }
+  }
+  if (c.paired && (c.wg == 0 || j + 1 < c.nkv)) named_bar_arrive(c.wg ? v2::kBarWg0 : v2::kBarWg1, 256);
+  WVN_TPH(3)
+
+  if (j > 0 && !waited_pv) mbar_wait(c.pv_done, (j - 1) & 1);  // P buffer free again (PV(j-1) retired)
+  // ---- P -> tensor memory: row = lane, 64 columns of packed bf16 pairs (A operand of P·V)
+  tmem_st32(c.tmem_p, sr[0]);
+  tmem_st32(c.tmem_p + 32, sr[1]);
+  tmem_st_wait();
+  tc_fence_before();
+  mbar_arrive(c.p_full);
+  WVN_TPH(4)
+#undef WVN_TPH
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(v2::kThreads, 1)
+attention2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                  const __grid_constant__ CUtensorMap tmap_vt, const AttnArgs args) {
+  using namespace v2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + v2::kOffBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;                     // [kStages]
+  uint64_t* k_empty = k_full + v2::kStages;        // [kStages]
+  uint64_t* v_full = k_empty + v2::kStages;        // [kStages]
+  uint64_t* v_empty = v_full + v2::kStages;        // [kStages]
+  uint64_t* s_full = v_empty + v2::kStages;        // [2]
+  uint64_t* s_free = s_full + 2;                   // [2]
+  uint64_t* p_full = s_full + 4;                   // [2]
+  uint64_t* pv_done = s_full + 6;                  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ntiles = args.npad / kTileQ;
+  const int qpair = args.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int bh = args.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int q_tile0 = 2 * qpair;
+  const bool has1 = q_tile0 + 1 < ntiles;  // odd tile counts: the last CTA of a (frame, head) owns a single query tile
+  const int nkv = ntiles;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("[wvn] attention: dynamic smem base not 1024B aligned\n");
+    __trap();
+  }
+  if (warp == v2::kWarpMma && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < v2::kStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_free[t], 128);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&pv_done[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == v2::kWarpTma) tmem_alloc(tmem_slot, v2::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == v2::kWarpTma) {
+    // -------------------------------------------------------------- TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(v2::kRegsAux));
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_q);
+      tma_prefetch_desc(&tmap_k);
+      tma_prefetch_desc(&tmap_vt);
+      const int row0 = bh * args.npad;
+      mbar_arrive_expect_tx(q_full, has1 ? 2 * kQBytes : kQBytes);
+      tma_load_2d(&tmap_q, q_full, smem + v2::kOffQ, 0, row0 + q_tile0 * kTileQ);
+      if (has1) tma_load_2d(&tmap_q, q_full, smem + v2::kOffQ + kQBytes, 0, row0 + (q_tile0 + 1) * kTileQ);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % v2::kStages;
+        const uint32_t ph = (j / v2::kStages) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], kKBytes);
+        tma_load_2d(&tmap_k, &k_full[st], smem + v2::kOffK + st * kKBytes, 0, row0 + j * kTileKV);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], kVBytes);
+        tma_load_2d(&tmap_vt, &v_full[st], smem + v2::kOffV + st * kVBytes, j * kTileKV, bh * kDh);
+        tma_load_2d(&tmap_vt, &v_full[st], smem + v2::kOffV + st * kVBytes + kVBytes / 2, j * kTileKV + 64, bh * kDh);
+      }
+    }
+  } else if (warp == v2::kWarpMma) {
+    // -------------------------------------------------------------- MMA issuer (both query tiles)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(v2::kRegsAux));
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV);  // 128 x 128
+      constexpr uint32_t idesc_o = make_idesc_bf16(kTileQ, kDh);      // 128 x 64
+      auto qk = [&](int t, int j) {  // S_t = Q_t K(j)^T
+        const uint64_t desc_q = make_sw128_kmajor_desc(smem_u32(smem + v2::kOffQ + t * kQBytes));
+        const uint64_t desc_k = make_sw128_kmajor_desc(smem_u32(smem + v2::kOffK + (j % v2::kStages) * kKBytes));
+        const uint32_t tmem_s = tmem_base + t * v2::kTileCols + kColS;
+#pragma unroll
+        for (int k = 0; k < kDh / 16; ++k) umma_bf16_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[t]);
+      };
+      auto pv = [&](int t, int j) {  // O_t += P_t(j) V(j)
+        const uint32_t v_addr = smem_u32(smem + v2::kOffV + (j % v2::kStages) * kVBytes);
+        const uint32_t tmem_o = tmem_base + t * v2::kTileCols + kColO;
+        const uint32_t tmem_p = tmem_base + t * v2::kTileCols + kColP;
+#pragma unroll
+        for (int ks = 0; ks < kTileKV / 16; ++ks) {
+          const uint64_t desc_v = make_sw128_kmajor_desc(v_addr + (ks >> 2) * (kVBytes / 2)) + 2 * (ks & 3);
+          umma_bf16_ts(tmem_o, tmem_p + 8 * ks, desc_v, idesc_o, (j | ks) != 0);
+        }
+        umma_commit(&pv_done[t]);
+      };
+#ifdef WVN_ATTN_TIMING
+      const bool timing = args.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+      long long tm[4] = {0, 0, 0, 0}, tprev = timing ? clock64() : 0;
+#define WVN_TM(i) if (timing) { const long long tn = clock64(); tm[i] += tn - tprev; tprev = tn; }
+#else
+#define WVN_TM(i)
+#endif
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      qk(0, 0);
+      if (has1) qk(1, 0);
+      umma_commit(&k_empty[0]);
+      if (nkv > 1) {
+        mbar_wait(&k_full[1 % v2::kStages], 0);
+        mbar_wait(&s_free[0], 0);
+        tc_fence_after();
+        qk(0, 1);
+        if (has1) {
+          mbar_wait(&s_free[1], 0);
+          tc_fence_after();
+          qk(1, 1);
+        }
+        umma_commit(&k_empty[1 % v2::kStages]);
+      }
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j % v2::kStages;
+        const uint32_t ph = (j / v2::kStages) & 1;
+        const int st2 = (j + 2) % v2::kStages;
+        const uint32_t ph2 = ((j + 2) / v2::kStages) & 1;
+        WVN_TM(3)
+        mbar_wait(&v_full[st], ph);
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        WVN_TM(0)
+        pv(0, j);
+        if (!has1) umma_commit(&v_empty[st]);
+        if (j + 2 < nkv) {
+          mbar_wait(&k_full[st2], ph2);
+          mbar_wait(&s_free[0], (j + 1) & 1);
+          tc_fence_after();
+          qk(0, j + 2);
+          if (!has1) umma_commit(&k_empty[st2]);
+        }
+        WVN_TM(1)
+        if (has1) {
+          mbar_wait(&p_full[1], j & 1);
+          tc_fence_after();
+          WVN_TM(2)
+          pv(1, j);
+          umma_commit(&v_empty[st]);
+          if (j + 2 < nkv) {
+            mbar_wait(&s_free[1], (j + 1) & 1);
+            tc_fence_after();
+            qk(1, j + 2);
+            umma_commit(&k_empty[st2]);
+          }
+        }
+      }
+#ifdef WVN_ATTN_TIMING
+      if (timing)
+        for (int i = 0; i < 4; ++i) args.timing[8 + i] = tm[i];
+#endif
+#undef WVN_TM
+    }
+  } else if (warp >= v2::kWarpAux0 && warp < v2::kWarpAux0 + 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(v2::kRegsAux));
+  } else {
+    // -------------------------------------------------------------- softmax / correction / epilogue
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(v2::kRegsSoftmax));
+    const int wg = (warp - v2::kWarpSoftmax0) >> 2;
+    if (wg == 0 || has1) {
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;  // row inside the query tile == TMEM lane
+      const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+      SoftmaxCtx2 c;
+      c.tmem_s = tmem_base + lane_base + wg * v2::kTileCols + kColS;
+      c.tmem_o = tmem_base + lane_base + wg * v2::kTileCols + kColO;
+      c.tmem_p = tmem_base + lane_base + wg * v2::kTileCols + kColP;
+      c.sl2 = args.scale_log2;
+      c.s_full = &s_full[wg]; c.s_free = &s_free[wg]; c.p_full = &p_full[wg]; c.pv_done = &pv_done[wg];
+      c.m_ref = -INFINITY;
+      c.l = 0.f;
+      c.wg = wg; c.nkv = nkv; c.paired = has1 && !args.no_token;
+#ifdef WVN_ATTN_TIMING
+      const bool timing = args.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == v2::kWarpSoftmax0 * 32;
+      long long tph[6] = {0, 0, 0, 0, 0, 0}, tprev = timing ? clock64() : 0;
+#else
+      constexpr bool timing = false;
+      long long* tph = nullptr;
+      long long tprev = 0;
+#endif
+#pragma unroll 1
+      for (int j = 0; j < nkv - 1; ++j) softmax_tile2<POLY, false>(c, j, kTileKV, tph, timing, tprev);
+      softmax_tile2<(POLY == 9 ? 9 : 0), true>(c, nkv - 1, args.n_valid - (nkv - 1) * kTileKV, tph, timing, tprev);
+#ifdef WVN_ATTN_TIMING
+      if (timing)
+        for (int i = 0; i < 6; ++i) args.timing[i] = tph[i];
+#endif
+
+      // ---- epilogue: O / l -> bf16 -> out[b, q, h*64 + d]
+      mbar_wait(c.pv_done, (nkv - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.f / c.l;
+      const int b = bh / args.heads;
+      const int h = bh - b * args.heads;
+      const long long q_idx = static_cast<long long>(b) * args.npad + (q_tile0 + wg) * kTileQ + row;
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + q_idx * args.ldo + h * kDh;
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        uint32_t r[32];
+        tmem_ld32(c.tmem_o + q * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[8 * t + i]) * inv_l;
+          st_global_v4(dst + q * 32 + 8 * t, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                       pack_bf16x2(f[6], f[7]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == v2::kWarpTma) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, v2::kTmemCols);
   }
 }
 
@@ -426,21 +848,50 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
     poly = e ? atoi(e) : kDefaultPoly;
     if ((poly < 0 || poly > 4) && poly != 9) poly = kDefaultPoly;
   }
-  dim3 grid(a.npad / kTileQ, static_cast<unsigned>(bh));
+  // $WVN_ATTN_IMPL: 2 (default) = one CTA per SM owning two query tiles with ordered softmax warpgroups;
+  // 1 = round 1's kernel (one query tile per CTA, 2 independent CTAs per SM), kept for A/B measurements
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("WVN_ATTN_IMPL");
+    impl = e ? atoi(e) : 2;
+    if (impl != 1 && impl != 2) impl = 2;
+  }
+  static int no_token = -1;  // $WVN_ATTN_TOKEN=0: let the two softmax warpgroups free-run (A/B of the exp-phase ordering)
+  if (no_token < 0) {
+    const char* e = getenv("WVN_ATTN_TOKEN");
+    no_token = (e && atoi(e) == 0) ? 1 : 0;
+  }
+  AttnArgs a2 = a;
+  a2.no_token = no_token;
+  const int ntiles = a.npad / kTileQ;
+  dim3 grid(impl == 2 ? (ntiles + 1) / 2 : ntiles, static_cast<unsigned>(bh));
+  const int threads = impl == 2 ? v2::kThreads : kThreads;
+  const uint32_t smem_bytes = impl == 2 ? v2::kSmemBytes : kSmemBytes;
   auto launch = [&](auto kern) -> int {
-    WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     prof_begin(PROF_ATTENTION, stream);
-    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, a);
+    kern<<<grid, threads, smem_bytes, stream>>>(tq, tk, tv, a2);
     prof_end(PROF_ATTENTION, stream);
     return WVN_OK;
   };
-  switch (poly) {
-    case 0: WVN_PROPAGATE(launch(attention_kernel<0>)); break;
-    case 1: WVN_PROPAGATE(launch(attention_kernel<1>)); break;
-    case 2: WVN_PROPAGATE(launch(attention_kernel<2>)); break;
-    case 3: WVN_PROPAGATE(launch(attention_kernel<3>)); break;
-    case 4: WVN_PROPAGATE(launch(attention_kernel<4>)); break;
-    default: WVN_PROPAGATE(launch(attention_kernel<9>)); break;
+  if (impl == 2) {
+    switch (poly) {
+      case 0: WVN_PROPAGATE(launch(attention2_kernel<0>)); break;
+      case 1: WVN_PROPAGATE(launch(attention2_kernel<1>)); break;
+      case 2: WVN_PROPAGATE(launch(attention2_kernel<2>)); break;
+      case 3: WVN_PROPAGATE(launch(attention2_kernel<3>)); break;
+      case 4: WVN_PROPAGATE(launch(attention2_kernel<4>)); break;
+      default: WVN_PROPAGATE(launch(attention2_kernel<9>)); break;
+    }
+  } else {
+    switch (poly) {
+      case 0: WVN_PROPAGATE(launch(attention_kernel<0>)); break;
+      case 1: WVN_PROPAGATE(launch(attention_kernel<1>)); break;
+      case 2: WVN_PROPAGATE(launch(attention_kernel<2>)); break;
+      case 3: WVN_PROPAGATE(launch(attention_kernel<3>)); break;
+      case 4: WVN_PROPAGATE(launch(attention_kernel<4>)); break;
+      default: WVN_PROPAGATE(launch(attention_kernel<9>)); break;
+    }
   }
   WVN_CHECK_LAUNCH("attention_kernel");
   return WVN_OK;

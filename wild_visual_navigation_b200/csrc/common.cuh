@@ -89,14 +89,52 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #define WVN_MBAR_TIMEOUT_CYCLES 4000000000ll
 #endif
 
+// Up to 2^16 try_waits in a 4-instruction loop (try_wait suspends the thread in hardware for a bounded,
+// implementation-defined time; an explicit suspend-time hint was measured to delay the wake-up — see DESIGN.md): the single-thread producer / MMA-issuer warps share their SM sub-partition with the
+// math warps, and every instruction they spin on is an issue slot taken from those (round 1: 30 % of all issued
+// instructions of the attention kernel were the 12-instruction wait loops of these two warps).
+#ifndef WVN_MBAR_HINT_NS
+#define WVN_MBAR_HINT_NS 0
+#endif
+#define WVN_STR2(x) #x
+#define WVN_STR(x) WVN_STR2(x)
+#if WVN_MBAR_HINT_NS > 0
+#define WVN_TRY_WAIT_PTX "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, " WVN_STR(WVN_MBAR_HINT_NS) ";\n\t"
+#else
+#define WVN_TRY_WAIT_PTX "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
+
+__device__ __forceinline__ bool mbar_try_wait_many(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 n;\n\t"
+      "mov.u32 n, 65536;\n\t"
+      "WVN_WAIT_LOOP:\n\t"
+      WVN_TRY_WAIT_PTX
+      "@p bra WVN_WAIT_DONE;\n\t"
+      "sub.u32 n, n, 1;\n\t"
+      "setp.ne.u32 p, n, 0;\n\t"
+      "@p bra WVN_WAIT_LOOP;\n\t"
+      "WVN_WAIT_DONE:\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  // p is true on success (branch taken) and false when the counter ran out (setp.ne gave false)
+  return ok != 0;
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+  const uint32_t addr = smem_u32(bar);
   const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && clock64() - t0 > WVN_MBAR_TIMEOUT_CYCLES) {
+  while (!mbar_try_wait_many(addr, parity)) {
+    if (clock64() - t0 > WVN_MBAR_TIMEOUT_CYCLES) {
       printf("[wvn] mbarrier timeout: block (%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, smem_u32(bar), parity);
+             threadIdx.x, addr, parity);
       __trap();
     }
   }
@@ -375,6 +413,9 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // Explicit shared-space 16-byte accesses (addresses from smem_u32): keeps the compiler from falling

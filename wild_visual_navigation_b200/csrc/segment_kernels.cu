@@ -349,7 +349,8 @@ adjacency_emit_kernel(const unsigned int* __restrict__ adj, long long* __restric
   if (r == 0)
     for (int i = 1; i <= 1024; ++i) row_off[i] += row_off[i - 1];
   __syncthreads();
-  if (r == 0) n_edges[b] = row_off[1024];
+  // the count is clamped to the caller's capacity; a negative value (-(true count)) flags the overflow
+  if (r == 0) n_edges[b] = row_off[1024] <= max_edges ? row_off[1024] : -row_off[1024];
   if (r < smax) {
     int o = row_off[r];
     long long* eb = edges + b * max_edges * 2;

@@ -44,11 +44,12 @@ class FeatureExtractor:
             raise ValueError(f"Extractor[{feature_type}] is outside the B200 hot path")
         if need_stego:
             self._stego = StegoInterface(device=device, input_size=input_size, run_crf=kwargs.get("run_crf", False),
-                                         run_clustering=kwargs.get("run_clustering", False),
+                                         run_clustering=kwargs.get("run_clustering", True),  # the reference's default (:51)
                                          n_image_clusters=kwargs.get("n_image_clusters", 20),
                                          head_state_dict=kwargs.get("head_state_dict"),
                                          backbone_state_dict=kwargs.get("state_dict"),
-                                         flip_tta=kwargs.get("flip_tta", True), **common)
+                                         flip_tta=kwargs.get("flip_tta", True),
+                                         kmeans_iters=kwargs.get("kmeans_iters", 10), **common)
             self._dino = self._stego._dino
             self._extractor = self._stego if feature_type == "stego" else self._dino
         else:
@@ -71,6 +72,11 @@ class FeatureExtractor:
     def segmentation_type(self):
         return self._segmentation_type
 
+    @property
+    def max_segments(self):
+        """Upper bound of segments per frame of the stego segmentation (rows of the padded ``feat`` per frame)."""
+        return self._stego.max_segments if self._stego is not None else None
+
     def change_device(self, device):
         self._device = device
         self._extractor.change_device(device)
@@ -89,6 +95,8 @@ class FeatureExtractor:
         if self._segmentation_type == "random":
             return None, feat, seg, None, dense
         ne = int(r["n_edges"][0].item())
+        if ne < 0:  # the kernel flags an edge-buffer overflow with -(true count) instead of dropping edges silently
+            raise RuntimeError(f"adjacency list has {-ne} edges, more than the buffer of {r['edges'].shape[1]}")
         edges = r["edges"][0, :ne].T.contiguous()
         center = r["centers"][0, :n]
         return edges, feat, seg, center, dense
@@ -109,8 +117,8 @@ class FeatureExtractor:
         if self._segmentation_type == "stego":
             self._stego.inference(img)
             seg = self._stego.cluster_segments[0].long().contiguous()
-            counts = ops.relabel(seg, self._stego._n_clusters)
-            smax = self._stego._n_clusters
+            smax = self._stego.max_segments
+            counts = ops.relabel(seg, smax)
             tokens = self._stego.code_tokens if self._feature_type == "stego" else self._stego.backbone_tokens
         elif self._segmentation_type == "grid":
             cell = kwargs.get("cell_size", 32)

@@ -6,7 +6,10 @@
 columns (weights.fold_stego_head) and evaluated at patch resolution, then one kernel does the
 bilinear(align_corners=False) upsampling + argmax per pixel — algebraically the upstream
 ``postprocess`` (upsample the 90-d code, then probe every pixel) without the 448x448x90 tensor.
-CRF and per-image k-means are not on the hot path (``run_crf`` / ``run_clustering`` must be False).
+``run_clustering=True`` (WVN's default through ``FeatureExtractor``): the cluster prediction comes from a per-image
+k-means of the code with ``n_image_clusters`` clusters (csrc/stego_kmeans.cu — one launch per batch of frames; the
+nearest-centroid scores replace the cluster-probe logits before the same upsample+argmax kernel).  CRF is out of scope
+(``run_crf`` must be False; the reference's own default for WVN, feature_extractor.py:52).
 """
 from __future__ import annotations
 
@@ -21,23 +24,23 @@ class StegoInterface:
     def __init__(self, device: str, input_size: int = 448, model_path: str = None, n_image_clusters: int = 40,
                  run_crf: bool = False, run_clustering: bool = False, cfg=None, backbone_type: str = "vit_small",
                  patch_size: int = 8, head_state_dict=None, backbone_state_dict=None, flip_tta: bool = True,
-                 max_batch: int = 32, chunk: int = 0, code_dim: int = 90):
+                 max_batch: int = 32, chunk: int = 0, code_dim: int = 90, kmeans_iters: int = 10):
         self._cfg = _Cfg(cfg) if cfg else _Cfg(model_path=model_path, input_size=input_size, run_crf=run_crf,
                                                run_clustering=run_clustering, n_image_clusters=n_image_clusters)
-        if self._cfg.run_crf or self._cfg.run_clustering:
-            raise ValueError("run_crf / run_clustering (CRF, per-image k-means) are outside the B200 hot path "
-                             "(SURVEY.md §8f rank 4); construct with both False")
+        if self._cfg.run_crf:
+            raise ValueError("run_crf (pydensecrf on the CPU) is outside the B200 hot path; WVN itself runs with "
+                             "run_crf=False (feature_extractor.py:52)")
+        self._kmeans_iters = kmeans_iters
         self._device = device
         self._flip_tta = flip_tta
         if head_state_dict is None:
             if model_path:
-                ck = torch.load(model_path, map_location="cpu")
+                # a STEGO Lightning checkpoint pickles OmegaConf hyper-parameters: needs the full unpickler (trusted file)
+                ck = torch.load(model_path, map_location="cpu", weights_only=False)
                 sd = ck.get("state_dict", ck)
                 head_state_dict = {k.replace("segmentation_head.", ""): v.squeeze(-1).squeeze(-1) if v.dim() == 4 else v
                                    for k, v in sd.items() if k.startswith(("segmentation_head.", "cluster_probe.",
                                                                            "linear_probe."))}
-                head_state_dict = {k.replace("cluster_probe.clusters", "cluster_probe.clusters"): v
-                                   for k, v in head_state_dict.items()}
                 if backbone_state_dict is None:
                     backbone_state_dict = {k.split("backbone.model.", 1)[1]: v for k, v in sd.items()
                                            if "backbone.model." in k} or None
@@ -47,6 +50,8 @@ class StegoInterface:
         self._head = head_state_dict
         self._code_dim = int(head_state_dict["cluster1.0.weight"].shape[0])
         self._n_clusters = int(head_state_dict["cluster_probe.clusters"].shape[0])
+        if self._cfg.run_clustering and not (1 <= self._cfg.n_image_clusters <= 64):
+            raise ValueError("n_image_clusters must be in [1, 64]")
         self._n_classes = int(head_state_dict["linear_probe.weight"].shape[0])
         self._dino = DinoInterface(device, input_size=input_size, backbone_type=backbone_type, patch_size=patch_size,
                                    max_batch=max_batch * (2 if flip_tta else 1), chunk=chunk,
@@ -86,7 +91,14 @@ class StegoInterface:
             self._tokens = vit.forward(img)
             head = vit.stego_head(B)
         S = self._cfg.input_size
-        cl, li = ops.logits_argmax(head, HEAD_CLUSTER_COL, self._n_clusters, B, npad, g, g, S, S,
+        n_cluster_logits = self._n_clusters
+        if self._cfg.run_clustering:
+            # per-image k-means of the code: the nearest-centroid scores overwrite the cluster-probe logit columns
+            n_cluster_logits = self._cfg.n_image_clusters
+            ops.check(ops.lib().wvn_stego_kmeans(ops.ptr(head), head.stride(0), B, npad, g * g, HEAD_CODE_COL,
+                                                 self._code_dim, HEAD_CLUSTER_COL, n_cluster_logits, self._kmeans_iters,
+                                                 None, ops.stream()))
+        cl, li = ops.logits_argmax(head, HEAD_CLUSTER_COL, n_cluster_logits, B, npad, g, g, S, S,
                                    col0_b=HEAD_LINEAR_COL, classes_b=self._n_classes)
         code = head.view(B, npad, -1)[:, 1 : 1 + g * g, HEAD_CODE_COL : HEAD_CODE_COL + self._code_dim].contiguous()
         self._code_tokens = code  # (B, P, 90) at patch resolution — what the fused consumers use
@@ -102,6 +114,11 @@ class StegoInterface:
     @property
     def model(self):
         return self._dino._model
+
+    @property
+    def max_segments(self):
+        """Upper bound of the cluster ids ``cluster_segments`` can hold (+1)."""
+        return self._cfg.n_image_clusters if self._cfg.run_clustering else self._n_clusters
 
     @property
     def input_size(self):

@@ -56,7 +56,7 @@ def load_dino_state_dict(backbone_type: str, patch_size: int, pretrained_weights
     shp = VIT_SHAPES[backbone_type]
     path = pretrained_weights or os.environ.get("WVN_DINO_WEIGHTS")
     if path:
-        sd = torch.load(path, map_location="cpu")
+        sd = torch.load(path, map_location="cpu", weights_only=False)  # DINO full checkpoints pickle argparse objects
         if "state_dict" in sd:
             sd = sd["state_dict"]
         if "teacher" in sd:

@@ -37,6 +37,13 @@ class SimpleMLP(torch.nn.Module):
     # ---- flat storage ---------------------------------------------------------------------
     def _flatten(self):
         ps = list(self.layers.parameters())
+        if self.flat_params is not None and ps and ps[0].device == self.flat_params.device:
+            off, same = 0, True
+            for p in ps:  # already views of the flat buffer (a second .to(same device) must not move the storage the
+                same &= p.data_ptr() == self.flat_params.data_ptr() + 4 * off  # CUDA trainer / inference handles hold)
+                off += p.numel()
+            if same:
+                return
         flat = torch.cat([p.detach().reshape(-1) for p in ps]).contiguous()
         off = 0
         for p in ps:

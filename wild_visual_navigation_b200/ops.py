@@ -85,7 +85,9 @@ def segment_reduce(seg, smax, tokens=None, grid=None, want_centers=True, want_ed
     centers = torch.empty(B, smax, 2, device=dev, dtype=torch.float32) if want_centers else None
     if want_edges:
         if max_edges is None:
-            max_edges = min(smax * smax, 8 * smax + 64)
+            # STEGO cluster labels are not connected regions: the directed label-pair count can reach smax*(smax-1),
+            # so the planar-graph bound only applies to large segment counts (SLIC-like, <= 1024 here: 16 MB worst case)
+            max_edges = smax * smax if smax <= 256 else min(smax * smax, 64 * smax)
         edges = torch.zeros(B, max_edges, 2, device=dev, dtype=torch.int64)
         n_edges = torch.zeros(B, device=dev, dtype=torch.int32)
     else:
@@ -273,16 +275,19 @@ def mlp_forward_f32(flat_params, x, dim, h1, h2):
 
 
 class MlpTrainer:
-    """Fused online train step on a flat fp32 parameter buffer (see csrc/mlp_train.cu).
+    """Fused online train step on a flat fp32 parameter buffer (csrc/mlp_train_fused.cu): four kernels, no host
+    synchronisation, rows may arrive padded per frame (``step_padded``) exactly as the segment pooling leaves them.
 
-    ``params`` is the tensor that SimpleMLP's layers view into, so the reference's state_dict
-    layout stays intact.  With ``process_group`` set, the confidence statistics and the flat
-    gradient are summed across ranks (one all-reduce each) for an exact global-batch step."""
+    ``params`` is the tensor that SimpleMLP's layers view into, so the reference's state_dict layout stays intact.
+    With ``process_group`` set the step is global-batch exact: the six statistic sums (incl. the row count) and the flat
+    gradient are all-reduced between the kernels — by the library's own NCCL communicator when the group's backend is
+    NCCL (one rank per GPU), otherwise (e.g. gloo in tests) by ``torch.distributed`` on the same buffers.
+    ``legacy=True`` runs round 1's three-phase kernels (csrc/mlp_train.cu), kept for A/B parity tests."""
 
     def __init__(self, params, dim=384, h1=256, h2=32, max_rows=4096, w_trav=0.03, w_reco=0.5, std_factor=0.5,
-                 anomaly_balanced=True, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+                 anomaly_balanced=True, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None, legacy=False):
         _C.require_device()
-        self.dim, self.h1, self.h2, self.max_rows = dim, h1, h2, max_rows
+        self.dim, self.h1, self.h2 = dim, h1, h2
         self.n_params = lib().wvn_mlp_param_count(dim, h1, h2)
         assert params.numel() == self.n_params and params.is_cuda and params.dtype == torch.float32
         dev = params.device
@@ -292,22 +297,98 @@ class MlpTrainer:
         self.exp_avg_sq = torch.zeros(self.n_params, device=dev)
         self.step_counter = torch.zeros(1, device=dev, dtype=torch.int64)
         self.cfg = TrainConfig(w_trav, w_reco, std_factor, int(anomaly_balanced), lr, betas[0], betas[1], eps)
-        self.scalars = torch.zeros(lib().wvn_mlp_train_scalars_bytes() // 8, device=dev, dtype=torch.float64)
         self.metrics = torch.zeros(6, device=dev)
         self.cg_mean = torch.zeros(1, device=dev)
         self.cg_std = torch.ones(1, device=dev)
         self.pg = process_group
-        self._alloc_ws(max_rows)
+        self.legacy = legacy
+        self._h = None
+        self._lib_comm = False
+        if legacy:
+            self.scalars = torch.zeros(lib().wvn_mlp_train_scalars_bytes() // 8, device=dev, dtype=torch.float64)
+            self._alloc_ws(max_rows)
+            return
+        self.scalars = torch.zeros((lib().wvn_mlp_trainer_scalars_bytes() + 7) // 8, device=dev, dtype=torch.float64)
+        self._create(max_rows)
 
+    # ---- fused path ---------------------------------------------------------------------------
+    def _create(self, max_rows):
+        if self._h is not None:
+            lib().wvn_mlp_trainer_destroy(self._h)
+            self._h = None
+        self.max_rows = int(max_rows)
+        h = c_void_p()
+        check(lib().wvn_mlp_trainer_create(self.dim, self.h1, self.h2, self.max_rows, byref(self.cfg), ptr(self.scalars),
+                                           ptr(self.grads), byref(h)))
+        self._h = h
+        self.conf = torch.empty(self.max_rows + 32, device=self.params.device, dtype=torch.float32)
+        self._lib_comm = False
+        if self.pg is not None:
+            import torch.distributed as dist
+
+            if dist.get_backend(self.pg) == "nccl":
+                # the library owns its communicator: rank 0 makes the id, torch.distributed only carries the 128 bytes
+                rank, world = dist.get_rank(self.pg), dist.get_world_size(self.pg)
+                buf = (ctypes.c_ubyte * 128)()
+                if rank == 0:
+                    check(lib().wvn_comm_unique_id(buf))
+                idt = torch.tensor(list(buf), dtype=torch.uint8, device=self.params.device)
+                dist.broadcast(idt, src=dist.get_global_rank(self.pg, 0), group=self.pg)
+                raw = (ctypes.c_ubyte * 128)(*idt.cpu().tolist())
+                check(lib().wvn_mlp_trainer_init_comm(self._h, raw, rank, world))
+                self._lib_comm = True
+
+    def _run(self, x, groups, rpg, n_rows, y, yv):
+        if groups * rpg > self.max_rows:
+            self._create(int(groups * rpg * 1.5))
+        x = x.contiguous()
+        y = y.contiguous().float()
+        yv = yv.contiguous().to(torch.uint8)
+        s = stream()
+
+        def phase(mask):
+            check(lib().wvn_mlp_train_step(self._h, ptr(self.params), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                           ptr(self.step_counter), ptr(x), groups, rpg, ptr(n_rows), ptr(y), ptr(yv),
+                                           ptr(self.cg_mean), ptr(self.cg_std), ptr(self.conf), ptr(self.metrics), mask, s))
+
+        if self.pg is None or self._lib_comm:
+            phase(7)
+        else:  # non-NCCL process group (tests): the same two exchanges through torch.distributed
+            import torch.distributed as dist
+
+            phase(1)
+            dist.all_reduce(self.scalars[:6], group=self.pg)
+            phase(2)
+            dist.all_reduce(self.grads, group=self.pg)
+            phase(4)
+
+    def step_padded(self, feat, n_rows, y, y_valid):
+        """feat [G, S, D] f32 padded per group, n_rows [G] int32 (device): the first n_rows[g] rows of group g are live.
+        y / y_valid are indexed by the compacted row number.  Returns the confidence buffer (compacted order; the live
+        prefix has sum(n_rows) entries — no host sync happens here)."""
+        assert not self.legacy
+        G, S, D = feat.shape
+        assert D == self.dim and n_rows.dtype == torch.int32 and y.numel() >= 1
+        self._run(feat, G, S, n_rows, y, y_valid)
+        return self.conf
+
+    def step(self, x, y, y_valid, n_total=None):
+        """x [R,D] f32, y [R] f32, y_valid [R] bool.  Returns the confidence vector [R]; metrics stay
+        on the device in ``self.metrics`` (loss_total, loss_trav, loss_reco, loss_trav_conf, mean, std)."""
+        if self.legacy:
+            return self._step_legacy(x, y, y_valid, n_total)
+        R = x.shape[0]
+        self._run(x, 1, R, None, y, y_valid)
+        return self.conf[:R]
+
+    # ---- round-1 kernels (three phases, ~20 launches) --------------------------------------------
     def _alloc_ws(self, max_rows):
         self.max_rows = max_rows
         nbytes = lib().wvn_mlp_train_workspace_bytes(self.dim, self.h1, self.h2, max_rows)
         self.ws = torch.empty(nbytes // 4, device=self.params.device, dtype=torch.float32)
         self.conf = torch.empty(max_rows, device=self.params.device, dtype=torch.float32)
 
-    def step(self, x, y, y_valid, n_total=None):
-        """x [R,D] f32, y [R] f32, y_valid [R] bool.  Returns the confidence vector [R]; metrics stay
-        on the device in ``self.metrics`` (loss_total, loss_trav, loss_reco, loss_trav_conf, mean, std)."""
+    def _step_legacy(self, x, y, y_valid, n_total=None):
         R = x.shape[0]
         if R > self.max_rows:
             self._alloc_ws(int(R * 1.5))
@@ -337,3 +418,11 @@ class MlpTrainer:
                                         ptr(self.step_counter), n_total, byref(self.cfg), ptr(self.scalars), s))
         check(lib().wvn_mlp_train_read_metrics(ptr(self.scalars), ptr(self.metrics), s))
         return self.conf[:R]
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().wvn_mlp_trainer_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -105,6 +105,8 @@ class TraversabilityEstimator:
         self._trainer = ops.MlpTrainer(m.flat_params, m.input_size, m.hidden[0], m.hidden[1], max_rows=max_rows,
                                        w_trav=lp["w_trav"], w_reco=lp["w_reco"], std_factor=cg.std_factor,
                                        anomaly_balanced=lp["anomaly_balanced"], lr=self._lr, process_group=process_group)
+        # the train step writes the ConfidenceGenerator's mean / std straight into the module's parameters
+        self._trainer.cg_mean, self._trainer.cg_std = cg.mean.data, cg.std.data
         self._loss = torch.tensor([torch.inf])
         self._step = 0
         self._last_confidence = None
@@ -153,9 +155,16 @@ class TraversabilityEstimator:
         on the device in ``self._trainer.metrics``; returns the per-row confidence."""
         with self._learning_lock:
             conf = self._trainer.step(graph.x, graph.y, graph.y_valid, n_total=n_total)
-            cg = self._traversability_loss._confidence_generator
-            cg.mean.data.copy_(self._trainer.cg_mean)
-            cg.std.data.copy_(self._trainer.cg_std)
+            self._last_confidence = conf
+        self._step += 1
+        return conf
+
+    def train_on_padded(self, feat, n_rows, y, y_valid):
+        """The same step on rows that are still padded per frame, as ``FeatureExtractor.extract_batch`` returns them:
+        ``feat`` (B, smax, D), ``n_rows`` (B,) int32 on the device; ``y`` / ``y_valid`` are indexed by the compacted row
+        number (what ``feat[mask]`` would give).  No host synchronisation (the gather happens inside the kernels)."""
+        with self._learning_lock:
+            conf = self._trainer.step_padded(feat, n_rows, y, y_valid)
             self._last_confidence = conf
         self._step += 1
         return conf

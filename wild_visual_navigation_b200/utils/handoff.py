@@ -27,9 +27,11 @@ def write_tmp_state_dict(model: torch.nn.Module, confidence_generator, path: str
         path = os.path.join(path, TMP_STATE_DICT_NAME)
     sd = model.state_dict()
     sd["confidence_generator"] = confidence_generator.get_dict()
-    if os.path.exists(path):
-        os.remove(path)
-    torch.save(sd, path)
+    # the reference removes the old file and saves in place (a reader can catch a half-written file); write next to
+    # it and rename instead — atomic on POSIX, and the reference's reader sees the same file name and format
+    tmp = path + ".writing"
+    torch.save(sd, tmp)
+    os.replace(tmp, path)
     return path
 
 
@@ -42,7 +44,10 @@ def read_tmp_state_dict(model: torch.nn.Module, confidence_generator, path: str)
         return False
     live = model.state_dict()
     device = next(iter(live.values())).device
-    new = torch.load(path, map_location=device, weights_only=False)
+    try:
+        new = torch.load(path, map_location=device, weights_only=False)  # trusted file written by the learner process
+    except Exception:  # a reference-side writer saves in place: a half-written file is "no update yet"
+        return False
     k = list(live.keys())[-1]
     if k not in new:  # a different model family wrote the file
         return False

@@ -21,7 +21,10 @@ class TraversabilityLoss(nn.Module):
         if trav_cross_entropy:
             raise ValueError("trav_cross_entropy is not supported on the B200 hot path (reference default: False)")
         self._w_trav, self._w_reco, self._w_temp = w_trav, w_reco, w_temp
-        self._model = [model]  # not registered as a sub-module (the reference stores the bare reference)
+        # registered as a sub-module exactly as the reference does (loss.py:74: ``self._model = model``), so that
+        # ``traversability_loss_state_dict`` carries ``_model.layers.{0,2,4}.{weight,bias}`` next to
+        # ``_confidence_generator.*`` and checkpoints interoperate with the reference in both directions
+        self._model = model
         self._anomaly_balanced = anomaly_balanced
         self._confidence_generator = ConfidenceGenerator(
             std_factor=confidence_std_factor, method=method, log_enabled=log_enabled, log_folder=log_folder)
