@@ -164,9 +164,11 @@ int wvn_logits_argmax(const float* logits, long long ld, int col0, int classes, 
  * [code_col, code_col+code_dim).  Lloyd iterations (Euclidean, `iters` fixed, evenly spaced deterministic init) over the
  * `patches` code rows of each frame; the per-patch nearest-centroid scores <x,c_k> - |c_k|^2/2 are written to columns
  * [logit_col, logit_col+k) so that wvn_logits_argmax yields the per-pixel labels of the upsampled code.
- * centroids_out: optional [batch, k, code_dim]. */
+ * centroids_out: optional [batch, k, code_dim]; workspace: wvn_stego_kmeans_workspace_bytes(batch, k, code_dim) bytes of device
+ * memory (partial sums of the 8 CTAs that share a frame; no initialisation needed).  One launch for all frames and iterations. */
+size_t wvn_stego_kmeans_workspace_bytes(int batch, int k, int code_dim);
 int wvn_stego_kmeans(float* rows, long long ld, int batch, int npad, int patches, int code_col, int code_dim, int logit_col,
-                     int k, int iters, float* centroids_out, void* stream);
+                     int k, int iters, float* centroids_out, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Segment reductions — replace SegmentExtractor.adjacency_list / .centers
@@ -206,6 +208,9 @@ int wvn_supervision_pool(const long long* seg, const float* mask, int batch, int
 typedef struct wvn_mlp_infer wvn_mlp_infer_t;
 int wvn_mlp_infer_create(int dim, int h1, int h2, int chunk_rows, wvn_mlp_infer_t** out);
 void wvn_mlp_infer_destroy(wvn_mlp_infer_t* h);
+/* Sizes the per-pixel path's workspaces for a token grid of `tokens_per_frame` patches, so that wvn_mlp_infer_pixels
+ * never allocates (call once after create; a later call with a larger grid grows them). */
+int wvn_mlp_infer_reserve(wvn_mlp_infer_t* h, int tokens_per_frame);
 /* params: flat fp32 buffer in state_dict order layers.0.weight, layers.0.bias, layers.2.weight,
  * layers.2.bias, layers.4.weight, layers.4.bias (device memory). */
 int wvn_mlp_infer_set_params(wvn_mlp_infer_t* h, const float* params, void* stream);

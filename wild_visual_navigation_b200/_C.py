@@ -58,13 +58,15 @@ SIGNATURES = {
     "wvn_vit_npad": (_I, [_P]),
     "wvn_upsample_dense": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "wvn_logits_argmax": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
-    "wvn_stego_kmeans": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "wvn_stego_kmeans_workspace_bytes": (_S, [_I, _I, _I]),
+    "wvn_stego_kmeans": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "wvn_segment_workspace_bytes": (_S, [_I, _I, _I, _I]),
     "wvn_segment_reduce": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
     "wvn_segment_relabel": (_I, [_P, _I, _L, _I, _P, _P, _P]),
     "wvn_supervision_pool": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "wvn_mlp_infer_create": (_I, [_I, _I, _I, _I, POINTER(_P)]),
     "wvn_mlp_infer_destroy": (None, [_P]),
+    "wvn_mlp_infer_reserve": (_I, [_P, _I]),
     "wvn_mlp_infer_set_params": (_I, [_P, _P, _P]),
     "wvn_mlp_infer_pixels": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P]),
     "wvn_mlp_infer_rows": (_I, [_P, _P, _L, _P, _P, _F, _P, _P, _P]),

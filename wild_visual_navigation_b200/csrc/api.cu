@@ -89,6 +89,8 @@ struct wvn_vit {
   DevBuf x, xn, q, k, vt, attn, hid, ape, stage;
   // per max_batch
   DevBuf tok_bf16, head_hidden;
+  DevBuf qkv_f32;        // only with $WVN_VIT_PRECISE=1 at create: fp32 QKV projections of one chunk (parity-debug attention)
+  bool precise = false;
   bool forwarded = false;
   int last_batch = 0;
 
@@ -267,6 +269,12 @@ int wvn_vit_create(const wvn_vit_config* cfg, wvn_vit_t** out) {
   alloc(h->stage, 8u << 20);
   alloc(h->tok_bf16, static_cast<size_t>(cfg->max_batch) * h->npad * D * 2);
   if (cfg->head_out > 0) alloc(h->head_hidden, static_cast<size_t>(cfg->max_batch) * h->npad * D * 2);
+  {
+    // parity-debug mode: Q K^T, softmax and P V in fp32 on fp32 projections, ~40x slower attention
+    const char* e = getenv("WVN_VIT_PRECISE");
+    h->precise = e && atoi(e) == 1;
+    if (h->precise) alloc(h->qkv_f32, rows * 3 * D * 4);
+  }
   if (rc != WVN_OK) {
     wvn_vit_destroy(h);
     return rc;
@@ -279,7 +287,7 @@ void wvn_vit_destroy(wvn_vit_t* h) {
   if (!h) return;
   for (auto& b : h->owned) b.release();
   for (DevBuf* b : {&h->x, &h->xn, &h->q, &h->k, &h->vt, &h->attn, &h->hid, &h->ape, &h->stage, &h->tok_bf16,
-                    &h->head_hidden})
+                    &h->head_hidden, &h->qkv_f32})
     b->release();
   delete h;
 }
@@ -426,6 +434,15 @@ int vit_forward_impl(wvn_vit_t* h, const void* img, bool u8_hwc, int src_batch, 
         ls.reverse = next_dir();
         WVN_PROPAGATE(layernorm_rows(x + roff * D, h->wp<float>(b + "norm1.weight"), h->wp<float>(b + "norm1.bias"),
                                      xn + roff * D, nullptr, ls, s));
+        if (h->precise) {
+          GemmArgs g;
+          float* qkv = reinterpret_cast<float*>(h->qkv_f32.p) + roff * 3 * D;
+          g.M = ns * h->npad; g.N = 3 * D; g.K = D; g.epi = EPI_F32; g.bias = h->wp<float>(b + "attn.qkv.bias");
+          g.out = qkv; g.ldo = 3 * D;
+          WVN_PROPAGATE(gemm_bf16(g, xn + roff * D, D, h->wp<void>(b + "attn.qkv.weight"), 0, s));
+          WVN_PROPAGATE(attention_f32_debug(qkv, attn + roff * D, ns, c.heads, h->npad, h->n_valid, D, 0.125f, s));
+          continue;
+        }
         GemmArgs g;
         g.M = ns * h->npad; g.N = 3 * D; g.K = D; g.epi = EPI_QKV; g.bias = h->wp<float>(b + "attn.qkv.bias");
         g.npad = h->npad; g.dim = D; g.heads = c.heads;
@@ -525,12 +542,14 @@ int wvn_logits_argmax(const float* logits, long long ld, int col0, int classes, 
   return logits_argmax(logits, seg, seg_b, a, S(stream));
 }
 
+size_t wvn_stego_kmeans_workspace_bytes(int batch, int k, int code_dim) { return stego_kmeans_workspace_bytes(batch, k, code_dim); }
+
 int wvn_stego_kmeans(float* rows, long long ld, int batch, int npad, int patches, int code_col, int code_dim, int logit_col,
-                     int k, int iters, float* centroids_out, void* stream) {
+                     int k, int iters, float* centroids_out, void* workspace, void* stream) {
   KmeansArgs a;
   a.batch = batch; a.npad = npad; a.patches = patches; a.ld = ld; a.code_col = code_col; a.code_dim = code_dim;
   a.logit_col = logit_col; a.k = k; a.iters = iters; a.centroids_out = centroids_out;
-  return stego_kmeans(rows, a, S(stream));
+  return stego_kmeans(rows, a, reinterpret_cast<float*>(workspace), S(stream));
 }
 
 // -------------------------------------------------------------------------------- segments
@@ -676,7 +695,6 @@ extern "C" {
 
 int wvn_mlp_infer_create(int dim, int h1, int h2, int chunk_rows, wvn_mlp_infer_t** out) {
   WVN_REQUIRE(out && dim > 0 && h1 > 0 && h2 > 0, "wvn_mlp_infer_create: bad arguments");
-  WVN_REQUIRE(dim % 4 == 0, "wvn_mlp_infer_create: dim must be a multiple of 4");
   WVN_PROPAGATE(wvn_check_device());
   wvn_mlp_infer* h = new wvn_mlp_infer();
   h->dim = dim; h->h1 = h1; h->h2 = h2;
@@ -725,6 +743,18 @@ void wvn_mlp_infer_destroy(wvn_mlp_infer_t* h) {
   delete h;
 }
 
+int wvn_mlp_infer_reserve(wvn_mlp_infer_t* h, int tokens_per_frame) {
+  WVN_REQUIRE(h && tokens_per_frame > 0, "wvn_mlp_infer_reserve: bad arguments");
+  const int P = tokens_per_frame;
+  if (h->fused_tokens >= kFusedFrames * P) return WVN_OK;
+  for (DevBuf* b : {&h->tok_bf16, &h->gu, &h->gram}) b->release();
+  WVN_PROPAGATE(h->tok_bf16.alloc(static_cast<size_t>(kFusedFrames) * P * h->dim_p * 2));
+  WVN_PROPAGATE(h->gu.alloc(static_cast<size_t>(kFusedFrames) * P * kPixelHeadN * 4));
+  WVN_PROPAGATE(h->gram.alloc(static_cast<size_t>(kFusedFrames) * P * 5 * 4));
+  h->fused_tokens = kFusedFrames * P;
+  return WVN_OK;
+}
+
 int wvn_mlp_infer_set_params(wvn_mlp_infer_t* h, const float* params, void* stream) {
   WVN_REQUIRE(h && params, "wvn_mlp_infer_set_params: null argument");
   MlpShape sh;
@@ -748,17 +778,14 @@ int wvn_mlp_infer_pixels(wvn_mlp_infer_t* h, const float* tokens, int batch, int
   WVN_REQUIRE(h && tokens && trav && conf && cg_mean && cg_std, "wvn_mlp_infer_pixels: null argument");
   if (!h->loaded) return set_error(WVN_ERR_STATE, "wvn_mlp_infer_pixels: parameters were never set");
   cudaStream_t s = S(stream);
-  const int ww = (h->force_unfused || h->dim % 64 != 0) ? 0 : pixel_head_supported(h->h1, h->h2, gh, gw, out_h, out_w);
+  // any feature width works (the 90-d STEGO code is zero-padded to 128 columns in the bf16 operands)
+  const int ww = h->force_unfused ? 0 : pixel_head_supported(h->h1, h->h2, gh, gw, out_h, out_w);
   if (ww > 0) {
     // ---- fused path: per-token GEMM (G | U | cT) + token Gram, then one kernel per chunk of frames
     const int P = gh * gw;
-    if (h->fused_tokens < kFusedFrames * P) {
-      for (DevBuf* b : {&h->tok_bf16, &h->gu, &h->gram}) b->release();
-      WVN_PROPAGATE(h->tok_bf16.alloc(static_cast<size_t>(kFusedFrames) * P * h->dim_p * 2));
-      WVN_PROPAGATE(h->gu.alloc(static_cast<size_t>(kFusedFrames) * P * kPixelHeadN * 4));
-      WVN_PROPAGATE(h->gram.alloc(static_cast<size_t>(kFusedFrames) * P * 5 * 4));
-      h->fused_tokens = kFusedFrames * P;
-    }
+    // workspaces are sized by wvn_mlp_infer_reserve (called by the owner right after create); a larger token grid
+    // than reserved grows them here once
+    if (h->fused_tokens < kFusedFrames * P) WVN_PROPAGATE(wvn_mlp_infer_reserve(h, P));
     for (int b0 = 0; b0 < batch; b0 += kFusedFrames) {
       const int nb = std::min(kFusedFrames, batch - b0);
       const long long rows = static_cast<long long>(nb) * P;

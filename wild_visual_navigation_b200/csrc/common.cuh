@@ -21,6 +21,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of the (fully converged) warp.  The single-thread roles (TMA producer, MMA issuer) run with ALL 32 lanes
+// in the loop and guard only the issue instructions with this: ptxas knows the predicate selects exactly one lane and
+// emits `ELECT; @P UTCHMMA`.  Under a plain `if (lane == 0)` the branch is divergent as far as the compiler can tell and
+// every uniform-datapath instruction (UTCHMMA, UTMALDG, UTCBAR) is wrapped in its own ELECT / BRA.U.ANY
+// serialisation loop preceded by R2UR moves — ~90 clk per tcgen05.mma issue, which made the attention kernel
+// MMA-ISSUE bound (12 small UMMAs per KV tile; round-2 SASS + phase timing).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -96,6 +96,16 @@ interp_pixel_rows_kernel(const float* __restrict__ tok, __nv_bfloat16* __restric
     const float4* r10 = reinterpret_cast<const float4*>(base + (static_cast<long long>(y1) * a.grid_w + x0) * a.dim);
     const float4* r11 = reinterpret_cast<const float4*>(base + (static_cast<long long>(y1) * a.grid_w + x1) * a.dim);
     __nv_bfloat16* dst = out + i * a.ld_out;
+    if (a.dim & 3) {  // rows are not 16-byte aligned (the 90-d STEGO code): scalar channels
+      const float* s00 = reinterpret_cast<const float*>(r00);
+      const float* s01 = reinterpret_cast<const float*>(r01);
+      const float* s10 = reinterpret_cast<const float*>(r10);
+      const float* s11 = reinterpret_cast<const float*>(r11);
+      for (int c = lane; c < a.dim; c += 32)
+        dst[c] = __float2bfloat16_rn((1.f - wy) * ((1.f - wx) * __ldg(s00 + c) + wx * __ldg(s01 + c)) +
+                                     wy * ((1.f - wx) * __ldg(s10 + c) + wx * __ldg(s11 + c)));
+      continue;
+    }
     for (int v = lane; v < vecs; v += 32) {
       const float4 a00 = __ldg(r00 + v), a01 = __ldg(r01 + v), a10 = __ldg(r10 + v), a11 = __ldg(r11 + v);
       float4 o;
@@ -173,7 +183,7 @@ int upsample_tokens_dense(const float* tokens, float* out, const DenseArgs& a, c
 
 int interp_pixel_rows(const float* tokens, void* out_bf16, const DenseArgs& a, long long pix0, long long npix,
                       cudaStream_t stream) {
-  WVN_REQUIRE(a.dim % 4 == 0 && a.ld_out >= a.dim && a.ld_out % 4 == 0, "interp_pixel_rows: bad dims");
+  WVN_REQUIRE(a.dim > 0 && a.ld_out >= a.dim && a.ld_out % 4 == 0, "interp_pixel_rows: bad dims");
   if (npix <= 0) return WVN_OK;
   long long blocks = (npix * 32 + 255) / 256;
   const long long max_blocks = static_cast<long long>(sm_count()) * 16;

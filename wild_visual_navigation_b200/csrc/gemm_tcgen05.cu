@@ -35,11 +35,18 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 16;                 // multiple of 4: kEpiGroups warps share each TMEM lane quarter
+// Warp roles: the sub-partition arbiter prefers the highest warp id among eligible warps, so the single-thread TMA /
+// MMA-issuer warps sit ABOVE the 16 epilogue warps (see attention_tcgen05.cu; -DWVN_GEMM_AUX_FIRST restores round 1's
+// layout with them at ids 0 / 1 for A/B runs).
+#ifdef WVN_GEMM_AUX_FIRST
+constexpr int kEpiWarp0 = 4, kWarpTma = 0, kWarpMma = 1, kWarpAlloc = 2;
+#else
+constexpr int kEpiWarp0 = 0, kWarpTma = kEpiWarps, kWarpMma = kEpiWarps + 1, kWarpAlloc = kEpiWarps + 2;
+#endif
 constexpr int kEpiGroups = kEpiWarps / 4;
 constexpr int kNumEpiThreads = kEpiWarps * 32;
-constexpr int kNumThreads = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr int kNumThreads = (4 + kEpiWarps) * 32;
 constexpr int kMaxSmemBytes = 227 * 1024;
 constexpr int kMaxStages = 8;
 
@@ -274,7 +281,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
   }
 }
 #ifdef WVN_GEMM_TIMING
-#define WVN_TM_DECL const bool timing = args.timing != nullptr && blockIdx.x == 0; long long tm[4] = {0, 0, 0, 0}, tprev = clock64(), ntiles = 0;
+#define WVN_TM_DECL
 #define WVN_TM(i) if (timing) { const long long tn = clock64(); tm[i] += tn - tprev; tprev = tn; }
 #define WVN_TM_TILE ++ntiles;
 #define WVN_TM_FLUSH if (timing) { for (int i = 0; i < 3; ++i) args.timing[i] = tm[i]; args.timing[3] = ntiles; }
@@ -316,11 +323,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int num_k = args.K / BK;
   constexpr bool ROW_OWNER = (EPI == EPI_MLP_HEAD);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -331,37 +338,45 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == kWarpAlloc) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+  if (warp == kWarpTma) {
+    // ------------------------------------------------------------------ TMA producer (whole warp in the loop, one
+    // elected lane issues — see elect_one_sync in common.cuh)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (TileIter<ROW_OWNER> it(num_m, num_n); it.valid(); it.next()) {
         const int m_eff = args.reverse_m ? num_m - 1 - it.m_blk : it.m_blk;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * BK, m_eff * BM);
-          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * BK, it.n_blk * BN);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * BK, m_eff * BM);
+            tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * BK, it.n_blk * BN);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+  } else if (warp == kWarpMma) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp waits, one elected
+    // lane issues the tcgen05.mma / commit instructions)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      WVN_TM_DECL
+#ifdef WVN_GEMM_TIMING
+      const bool timing = args.timing != nullptr && blockIdx.x == 0 && lane == 0;
+      long long tm[4] = {0, 0, 0, 0}, tprev = clock64(), ntiles = 0;
+#endif
       for (TileIter<ROW_OWNER> it(num_m, num_n); it.valid(); it.next()) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -371,24 +386,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           WVN_TM(1)
-          const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+          if (elect_one_sync()) {
+            const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
+            const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in (addr>>4) units
-            umma_bf16_ss(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in (addr>>4) units
+              umma_bf16_ss(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);                     // smem slot reusable once these MMAs retire
+            if (kb == num_k - 1) umma_commit(&acc_full[acc]);   // accumulator complete -> epilogue
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           WVN_TM(2)
         }
-        umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         WVN_TM_TILE
       }
       WVN_TM_FLUSH
     }
-  } else if (warp >= kEpiWarp0) {
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
     // ------------------------------------------------------------------ epilogue
     const int ewarp = warp - kEpiWarp0;
     const int row_in_tile = (ewarp & 3) * 32 + lane;
@@ -450,7 +468,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == kWarpAlloc) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }

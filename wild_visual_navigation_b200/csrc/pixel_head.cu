@@ -265,17 +265,19 @@ pixel_head_kernel(const __grid_constant__ CUtensorMap tmap_w2, const PixelHeadAr
 
     if (warp >= 4) {
       // ---------------- layer 2 on the tensor core: D[128, 32] = h1[128, 256] @ W2^T
-      if (threadIdx.x == 128) {
+      if (warp == 4) {  // whole warp waits, one elected lane issues (see elect_one_sync in common.cuh)
         mbar_wait(w2_full, 0);
         tc_fence_after();
-        constexpr uint32_t idesc = make_idesc_bf16(128, kH2);
+        if (elect_one_sync()) {
+          constexpr uint32_t idesc = make_idesc_bf16(128, kH2);
 #pragma unroll
-        for (int ks = 0; ks < kH1 / 16; ++ks) {
-          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem + kOffA + (ks >> 2) * 16384)) + 2 * (ks & 3);
-          const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem + kOffW2 + (ks >> 2) * 4096)) + 2 * (ks & 3);
-          umma_bf16_ss(tmem_d, da, db, idesc, ks != 0);
+          for (int ks = 0; ks < kH1 / 16; ++ks) {
+            const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem + kOffA + (ks >> 2) * 16384)) + 2 * (ks & 3);
+            const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem + kOffW2 + (ks >> 2) * 4096)) + 2 * (ks & 3);
+            umma_bf16_ss(tmem_d, da, db, idesc, ks != 0);
+          }
+          umma_commit(mma_done);
         }
-        umma_commit(mma_done);
       }
       __syncwarp();
       // ---------------- producers: once the consumers have taken what they need from gv / n2 / the pixel

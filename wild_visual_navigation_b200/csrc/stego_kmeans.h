@@ -14,8 +14,11 @@ struct KmeansArgs {
   int logit_col = 0;   // per-patch nearest-centroid scores are written to [logit_col, logit_col + k)
   int k = 0, iters = 0;
   float* centroids_out = nullptr;   // optional [batch, k, code_dim]
+  int n_priv = 0;                   // set by stego_kmeans(): warp-private sum copies per CTA
 };
 
-int stego_kmeans(float* rows, const KmeansArgs& a, cudaStream_t stream);
+// workspace: stego_kmeans_workspace_bytes(batch, k, code_dim) bytes of device memory (per-CTA partial sums).
+size_t stego_kmeans_workspace_bytes(int batch, int k, int code_dim);
+int stego_kmeans(float* rows, const KmeansArgs& a, float* workspace, cudaStream_t stream);
 
 }  // namespace wvn

@@ -136,6 +136,72 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ gam
   }
 }
 
+
+// ---- parity-debug attention (SURVEY.md §7 "an fp32 mode kept for debugging parity"; $WVN_VIT_PRECISE=1) ----------------
+// softmax(q k^T * scale) v in fp32 CUDA-core arithmetic on the fp32 QKV projections: no bf16 rounding of q, k, v, of the
+// scores or of P.  One thread = one query row (q and the output accumulator in registers), K / V tiles of 64 keys staged
+// in shared memory, online softmax per 16-key chunk.  ~40x slower than the tcgen05 kernel; it exists to separate
+// "kernel bug" from "bf16 rounding of peaked attention logits" (tests/test_path_gpu.py::test_vit_base_default_std...).
+__global__ void __launch_bounds__(128)
+attention_f32_debug_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int npad, int n_valid, int heads,
+                           int dim, float scale) {
+  __shared__ float ks[64][65];
+  __shared__ float vs[64][65];
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int qi = blockIdx.x * 128 + threadIdx.x;
+  const long long row0 = static_cast<long long>(b) * npad;
+  const int ld = 3 * dim;
+  float q[64], o[64];
+  const bool active = qi < npad;
+#pragma unroll
+  for (int d = 0; d < 64; ++d) {
+    q[d] = active ? qkv[(row0 + qi) * ld + h * 64 + d] * scale : 0.f;
+    o[d] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < n_valid; k0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 64; i += 128) {
+      const int kk = i >> 6, d = i & 63;
+      const bool ok = k0 + kk < n_valid;
+      ks[kk][d] = ok ? qkv[(row0 + k0 + kk) * ld + dim + h * 64 + d] : 0.f;
+      vs[kk][d] = ok ? qkv[(row0 + k0 + kk) * ld + 2 * dim + h * 64 + d] : 0.f;
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      float sc[16], cmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < 64; ++d) acc = fmaf(q[d], ks[c0 + j][d], acc);
+        sc[j] = (k0 + c0 + j < n_valid) ? acc : -INFINITY;
+        cmax = fmaxf(cmax, sc[j]);
+      }
+      if (cmax == -INFINITY) continue;
+      const float m_new = fmaxf(m, cmax);
+      const float alpha = expf(m - m_new);   // exp(-inf) = 0 on the first chunk
+      l *= alpha;
+#pragma unroll
+      for (int d = 0; d < 64; ++d) o[d] *= alpha;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float p = expf(sc[j] - m_new);
+        l += p;
+#pragma unroll
+        for (int d = 0; d < 64; ++d) o[d] = fmaf(p, vs[c0 + j][d], o[d]);
+      }
+      m = m_new;
+    }
+  }
+  if (active) {
+    const float inv = 1.f / l;
+    __nv_bfloat16* dst = out + (row0 + qi) * dim + h * 64;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) dst[d] = __float2bfloat16_rn(o[d] * inv);
+  }
+}
+
 }  // namespace
 
 int image_to_patches(const void* img, bool u8_hwc, void* out_bf16, const ImagePatchArgs& a, cudaStream_t stream) {
@@ -180,6 +246,16 @@ int layernorm_rows(const float* x, const float* gamma, const float* beta, void* 
     layernorm_rows_kernel<6><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
         x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, a);
   WVN_CHECK_LAUNCH("layernorm_rows_kernel");
+  return WVN_OK;
+}
+
+int attention_f32_debug(const float* qkv, void* out_bf16, int batch, int heads, int npad, int n_valid, int dim, float scale,
+                        cudaStream_t stream) {
+  WVN_REQUIRE(dim == heads * 64, "attention_f32_debug: head dim must be 64");
+  dim3 grid((npad + 127) / 128, heads, batch);
+  attention_f32_debug_kernel<<<grid, 128, 0, stream>>>(qkv, reinterpret_cast<__nv_bfloat16*>(out_bf16), npad, n_valid, heads,
+                                                      dim, scale);
+  WVN_CHECK_LAUNCH("attention_f32_debug_kernel");
   return WVN_OK;
 }
 

@@ -36,4 +36,8 @@ int init_token_rows(float* x, const float* cls, const float* pos, int batch, int
 int layernorm_rows(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
                    const LayerNormArgs& a, cudaStream_t stream);
 
+// Parity-debug attention in fp32 ($WVN_VIT_PRECISE=1): qkv [batch*npad, 3*dim] fp32 -> out [batch*npad, dim] bf16.
+int attention_f32_debug(const float* qkv, void* out_bf16, int batch, int heads, int npad, int n_valid, int dim, float scale,
+                        cudaStream_t stream);
+
 }  // namespace wvn

@@ -115,8 +115,10 @@ class FeatureExtractor:
         # 1. segmentation (+ the one backbone pass)
         tokens = None
         if self._segmentation_type == "stego":
-            self._stego.inference(img)
-            seg = self._stego.cluster_segments[0].long().contiguous()
+            self._stego._forward(img, want_linear=False)
+            # relabelled in place, as in the reference (segment_stego's loop mutates the interface's tensor too: `.to` on
+            # the same device returns it, feature_extractor.py:240-246)
+            seg = self._stego.cluster_ids.contiguous()
             smax = self._stego.max_segments
             counts = ops.relabel(seg, smax)
             tokens = self._stego.code_tokens if self._feature_type == "stego" else self._stego.backbone_tokens
@@ -143,7 +145,7 @@ class FeatureExtractor:
         # 2. features
         if tokens is None:
             if self._feature_type == "stego":
-                self._stego.inference(img)
+                self._stego._forward(img, want_linear=False)
                 tokens = self._stego.code_tokens
             else:
                 tokens = self._dino.inference_tokens(img)

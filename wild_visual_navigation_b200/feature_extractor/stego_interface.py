@@ -56,7 +56,7 @@ class StegoInterface:
         self._dino = DinoInterface(device, input_size=input_size, backbone_type=backbone_type, patch_size=patch_size,
                                    max_batch=max_batch * (2 if flip_tta else 1), chunk=chunk,
                                    state_dict=backbone_state_dict, head_weights=fold_stego_head(head_state_dict))
-        self._code = self._cluster_pred = self._linear_pred = None
+        self._code = self._cluster_pred = self._linear_pred = self._head_out = self._cl64 = self._li64 = self._code_tok = None
         self._tokens = None
 
     def change_device(self, device):
@@ -67,6 +67,14 @@ class StegoInterface:
         """img (B,3,H,W) -> (linear_pred, cluster_pred), each (1,B,H,H) int32 like the reference.
         Camera frames (B,H0,W0,3) uint8 are accepted too: they are resized (NEAREST) / center-cropped to
         ``input_size`` inside the patch loader, i.e. H = W = input_size as after ``ImageProjector.resize_image``."""
+        self._forward(img, want_linear=True)
+        return self.linear_segments, self.cluster_segments
+
+    @torch.no_grad()
+    def _forward(self, img: torch.Tensor, want_linear: bool):
+        """Backbone + head (+ per-image k-means) + per-pixel cluster argmax.  ``FeatureExtractor`` calls this with
+        ``want_linear=False``: WVN only consumes ``cluster_segments`` (feature_extractor.py:237-249), so the linear-probe
+        argmax, the int32 copies and the contiguous code tensor are produced lazily by the properties below."""
         if img.dtype == torch.uint8:
             img = img.to(self._device)
             B, H, W = img.shape[0], self._cfg.input_size, self._cfg.input_size
@@ -95,21 +103,24 @@ class StegoInterface:
         if self._cfg.run_clustering:
             # per-image k-means of the code: the nearest-centroid scores overwrite the cluster-probe logit columns
             n_cluster_logits = self._cfg.n_image_clusters
-            ops.check(ops.lib().wvn_stego_kmeans(ops.ptr(head), head.stride(0), B, npad, g * g, HEAD_CODE_COL,
-                                                 self._code_dim, HEAD_CLUSTER_COL, n_cluster_logits, self._kmeans_iters,
-                                                 None, ops.stream()))
-        cl, li = ops.logits_argmax(head, HEAD_CLUSTER_COL, n_cluster_logits, B, npad, g, g, S, S,
-                                   col0_b=HEAD_LINEAR_COL, classes_b=self._n_classes)
-        code = head.view(B, npad, -1)[:, 1 : 1 + g * g, HEAD_CODE_COL : HEAD_CODE_COL + self._code_dim].contiguous()
-        self._code_tokens = code  # (B, P, 90) at patch resolution — what the fused consumers use
-        self._code = None         # dense (B,90,H,H) only on demand (property `features`)
+            ops.stego_kmeans(head, B, npad, g * g, HEAD_CODE_COL, self._code_dim, HEAD_CLUSTER_COL, n_cluster_logits,
+                             self._kmeans_iters)
+        self._head_out, self._geom = head, (B, H, npad, g, S)
+        self._code_tok = self._code = self._cluster_pred = self._linear_pred = self._li64 = None
+        if want_linear:
+            cl, li = ops.logits_argmax(head, HEAD_CLUSTER_COL, n_cluster_logits, B, npad, g, g, S, S,
+                                       col0_b=HEAD_LINEAR_COL, classes_b=self._n_classes)
+            self._li64 = self._to_image_size(li)
+        else:
+            cl = ops.logits_argmax(head, HEAD_CLUSTER_COL, n_cluster_logits, B, npad, g, g, S, S)
+        self._cl64 = self._to_image_size(cl)   # (B, H, H) int64 cluster ids
         self._img_hw = (H, W)
-        if (S, S) != (H, H):
-            cl = torch.nn.functional.interpolate(cl[None].float(), (H, H), mode="nearest")[0].long()
-            li = torch.nn.functional.interpolate(li[None].float(), (H, H), mode="nearest")[0].long()
-        self._cluster_pred = cl[None].int()
-        self._linear_pred = li[None].int()
-        return self._linear_pred, self._cluster_pred
+
+    def _to_image_size(self, pred):
+        B, H, npad, g, S = self._geom
+        if (S, S) != (H, H):  # stego_interface.py:108-109: predictions go to (H, H) with 'nearest'
+            pred = torch.nn.functional.interpolate(pred[None].float(), (H, H), mode="nearest")[0].long()
+        return pred
 
     @property
     def model(self):
@@ -126,15 +137,32 @@ class StegoInterface:
 
     @property
     def linear_segments(self):
+        if self._linear_pred is None and self._head_out is not None:
+            if self._li64 is None:
+                B, H, npad, g, S = self._geom
+                self._li64 = self._to_image_size(ops.logits_argmax(self._head_out, HEAD_LINEAR_COL, self._n_classes, B, npad,
+                                                                   g, g, S, S))
+            self._linear_pred = self._li64[None].int()
         return self._linear_pred
 
     @property
     def cluster_segments(self):
+        if self._cluster_pred is None and self._head_out is not None:
+            self._cluster_pred = self._cl64[None].int()
         return self._cluster_pred
 
     @property
+    def cluster_ids(self):
+        """(B, H, H) int64 cluster ids — the form the segment kernels consume (no int32 round trip)."""
+        return self._cl64
+
+    @property
     def code_tokens(self):
-        return self._code_tokens
+        """(B, P, 90) fp32 code at patch resolution — what the fused consumers use."""
+        if self._code_tok is None and self._head_out is not None:
+            B, H, npad, g, S = self._geom
+            self._code_tok = self._head_out.view(B, npad, -1)[:, 1 : 1 + g * g, HEAD_CODE_COL : HEAD_CODE_COL + self._code_dim].contiguous()
+        return self._code_tok
 
     @property
     def backbone_tokens(self):
@@ -146,5 +174,5 @@ class StegoInterface:
         if self._code is None:
             g = self._dino.grid
             H = self._img_hw[0]
-            self._code = ops.upsample_dense(self._code_tokens, g, g, H, H)
+            self._code = ops.upsample_dense(self.code_tokens, g, g, H, H)
         return self._code

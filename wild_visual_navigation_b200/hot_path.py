@@ -23,7 +23,7 @@ from .traversability_estimator import TraversabilityEstimator
 class HotPathStep:
     def __init__(self, device: str, state_dict, head_state_dict, batch: int = 32, input_size: int = 448,
                  backbone_type: str = "vit_small", patch_size: int = 8, chunk: int = 32, flip_tta: bool = False,
-                 run_clustering: bool = False, n_image_clusters: int = 20, process_group=None, feature_type: str = "dino"):
+                 run_clustering: bool = True, n_image_clusters: int = 20, process_group=None, feature_type: str = "dino"):
         self.device, self.batch, self.input_size = device, batch, input_size
         self.fe = FeatureExtractor(device, segmentation_type="stego", feature_type=feature_type, input_size=input_size,
                                    state_dict=state_dict, head_state_dict=head_state_dict, flip_tta=flip_tta,
@@ -52,3 +52,31 @@ class HotPathStep:
         self.ti.refresh_weights()                                              # inference sees the updated MLP
         r["trav"], r["conf"], r["confidence_rows"] = trav, conf, crow
         return r
+
+    # ---- CUDA-graph replay of the whole step (the deployment case: one camera frame at a time, where ~120 launches per
+    # frame are launch-latency bound).  Everything the step enqueues — the library's kernels, its memsets and the few
+    # torch glue ops — is capturable: no host synchronisation, no allocation inside the library after create.
+    def capture(self, img: torch.Tensor, y: torch.Tensor, y_valid: torch.Tensor, warmup: int = 2):
+        """Captures ``step`` for inputs of this shape; afterwards ``replay(img)`` re-runs it on new frames."""
+        self._g_img, self._g_y, self._g_yv = img.clone(), y.clone(), y_valid.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(self._g_img, self._g_y, self._g_yv)
+        torch.cuda.current_stream().wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_out = self.step(self._g_img, self._g_y, self._g_yv)
+        return self._g_out
+
+    def replay(self, img: torch.Tensor, y: torch.Tensor = None, y_valid: torch.Tensor = None) -> dict:
+        """New frames (and optionally labels) through the captured step; returns the same (static) output tensors."""
+        self._g_img.copy_(img, non_blocking=True)
+        if y is not None:
+            self._g_y.copy_(y, non_blocking=True)
+            self._g_yv.copy_(y_valid, non_blocking=True)
+        self._graph.replay()
+        self.te._step += 1
+        return self._g_out
+

@@ -25,7 +25,8 @@ class TraversabilityInference:
         self._dino = dino
         self._model = model
         self._cg = confidence_generator
-        self._mlp = ops.MlpInference(model.input_size, model.hidden[0], model.hidden[1], chunk_rows)
+        self._mlp = ops.MlpInference(model.input_size, model.hidden[0], model.hidden[1], chunk_rows,
+                                       tokens_per_frame=dino.grid * dino.grid)
         self.refresh_weights()
 
     def refresh_weights(self):

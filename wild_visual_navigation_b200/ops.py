@@ -68,9 +68,24 @@ def logits_argmax(logits, col0, classes, batch, npad, gh, gw, out_h, out_w, col0
     return seg if seg_b is None else (seg, seg_b)
 
 
+_WS_CACHE = {}
+
+
+def _workspace(tag, nbytes, device):
+    """Scratch that the kernels fully (re)initialise themselves: one buffer per (tag, device), grown on demand, so the
+    per-frame calls do not allocate."""
+    key = (tag, str(device))
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1), device=device, dtype=torch.uint8)
+        _WS_CACHE[key] = buf
+    return buf
+
+
 def segment_reduce(seg, smax, tokens=None, grid=None, want_centers=True, want_edges=True, max_edges=None):
     """seg: [B,H,W] int64.  Returns dict(feat [B,smax,D] | None, centers [B,smax,2] | None,
-    edges [B,max_edges,2] | None, n_edges [B] int32 | None)."""
+    edges [B,max_edges,2] | None, n_edges [B] int32 | None).  Only the first n_edges[b] rows of edges[b] are written
+    (n_edges[b] < 0 flags an overflow of max_edges)."""
     B, H, W = seg.shape
     dev = seg.device
     if tokens is not None:
@@ -80,7 +95,7 @@ def segment_reduce(seg, smax, tokens=None, grid=None, want_centers=True, want_ed
         gh = gw = 1
         D = 0
     ws_bytes = lib().wvn_segment_workspace_bytes(B, smax, gh, gw)
-    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    ws = _workspace("segment_reduce", ws_bytes, dev)
     feat = torch.empty(B, smax, D, device=dev, dtype=torch.float32) if tokens is not None else None
     centers = torch.empty(B, smax, 2, device=dev, dtype=torch.float32) if want_centers else None
     if want_edges:
@@ -88,8 +103,8 @@ def segment_reduce(seg, smax, tokens=None, grid=None, want_centers=True, want_ed
             # STEGO cluster labels are not connected regions: the directed label-pair count can reach smax*(smax-1),
             # so the planar-graph bound only applies to large segment counts (SLIC-like, <= 1024 here: 16 MB worst case)
             max_edges = smax * smax if smax <= 256 else min(smax * smax, 64 * smax)
-        edges = torch.zeros(B, max_edges, 2, device=dev, dtype=torch.int64)
-        n_edges = torch.zeros(B, device=dev, dtype=torch.int32)
+        edges = torch.empty(B, max_edges, 2, device=dev, dtype=torch.int64)
+        n_edges = torch.empty(B, device=dev, dtype=torch.int32)
     else:
         max_edges, edges, n_edges = 0, None, None
     check(lib().wvn_segment_reduce(ptr(seg), B, H, W, smax, ptr(tokens), gh, gw, D, ptr(feat), ptr(centers), ptr(edges),
@@ -113,10 +128,18 @@ def pool_supervision(seg: torch.Tensor, mask: torch.Tensor, smax: int):
     return y, valid.bool()
 
 
+def stego_kmeans(head, batch, npad, patches, code_col, code_dim, logit_col, k, iters, centroids_out=None):
+    """Per-image k-means of the code columns of the head output ``head`` [batch*npad, ld]; leaves the per-patch
+    nearest-centroid scores in columns [logit_col, logit_col + k) (see include/wvn_b200.h)."""
+    ws = _workspace("stego_kmeans", lib().wvn_stego_kmeans_workspace_bytes(batch, k, code_dim), head.device)
+    check(lib().wvn_stego_kmeans(ptr(head), head.stride(0), batch, npad, patches, code_col, code_dim, logit_col, k, iters,
+                                 ptr(centroids_out), ptr(ws), stream()))
+
+
 def relabel(seg, num_labels):
     """In-place relabel of each frame of seg [B,H,W] to 0..S-1; returns counts [B] int32."""
     B = seg.shape[0]
-    scratch = torch.empty(B * num_labels, device=seg.device, dtype=torch.int32)
+    scratch = _workspace("relabel", 4 * B * num_labels, seg.device).view(torch.int32)[: B * num_labels]
     counts = torch.empty(B, device=seg.device, dtype=torch.int32)
     check(lib().wvn_segment_relabel(ptr(seg), B, seg[0].numel(), num_labels, ptr(scratch), ptr(counts), stream()))
     return counts
@@ -226,12 +249,14 @@ def _resized_size(h, w, size):
 # traversability MLP: inference handle and trainer
 # --------------------------------------------------------------------------------------------
 class MlpInference:
-    def __init__(self, dim=384, h1=256, h2=32, chunk_rows=0):
+    def __init__(self, dim=384, h1=256, h2=32, chunk_rows=0, tokens_per_frame=0):
         _C.require_device()
         self.dim, self.h1, self.h2 = dim, h1, h2
         h = c_void_p()
         check(lib().wvn_mlp_infer_create(dim, h1, h2, chunk_rows, byref(h)))
         self._h = h
+        if tokens_per_frame > 0:  # all workspaces exist before the first frame arrives
+            check(lib().wvn_mlp_infer_reserve(h, tokens_per_frame))
 
     def set_params(self, flat_params: torch.Tensor):
         assert flat_params.is_cuda and flat_params.dtype == torch.float32

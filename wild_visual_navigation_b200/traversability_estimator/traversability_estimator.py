@@ -238,7 +238,7 @@ class TraversabilityEstimator:
     def load_checkpoint(self, checkpoint_path: str):
         with self._learning_lock:
             self._pause_training = True
-            checkpoint = torch.load(checkpoint_path, map_location=self._device)
+            checkpoint = torch.load(checkpoint_path, map_location=self._device, weights_only=False)  # trusted mission file
             self._model.load_state_dict(checkpoint["model_state_dict"])
             self._load_optimizer_state_dict(checkpoint["optimizer_state_dict"])
             self._traversability_loss.load_state_dict(checkpoint["traversability_loss_state_dict"])
