@@ -450,8 +450,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (0 = the config's)")
     ap.add_argument("--chunk", type=int, default=32, help="frames per ViT activation chunk")
     ap.add_argument("--cpu-frames", type=int, default=1, help="frames per step of the bounded CPU sample (~3-6 s per frame)")
-    ap.add_argument("--cpu-threads", type=int, default=0,
-                    help="torch CPU threads for the CPU legs (0 = all host cores)")
+    ap.add_argument("--cpu-threads", type=int, default=32,
+                    help="torch CPU threads for the CPU legs (0 = all host cores).  Measured on the 128-thread B200 host: the "
+                         "eager oracle runs 1 frame in ~3 s on 32 threads and in 42 s on 128 (thread sync on its many small "
+                         "ops), so 32 is what 'all the threads it can use' means for this code")
     ap.add_argument("--gpu-eager-frames", type=int, default=2, help="frames per step of the GPU-eager oracle leg (0 = skip)")
     ap.add_argument("--no-extras", action="store_true", help="skip the latency / flip-TTA / GPU-eager legs")
     ap.add_argument("--profile-only", action="store_true", help="setup + warmup + steps only (for ncu)")

@@ -55,5 +55,6 @@ def cpu_step(imgs: torch.Tensor, sd: dict, cfg: ViTConfig, hd: dict, mlp_sd: dic
     if train:
         x = torch.cat(rows, dim=0)
         y, yv = wvn_path.synthetic_supervision(x.shape[0], seed=supervision_seed)
+        y, yv = y.to(x.device), yv.to(x.device)
         mlp_sd, opt_state, metrics = wvn_path.train_step(mlp_sd, opt_state, x, y, yv, lr=1e-3, std_factor=std_factor)
     return torch.stack(travs), torch.stack(confs), mlp_sd, opt_state, metrics

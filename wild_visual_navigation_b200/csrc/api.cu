@@ -188,6 +188,10 @@ int wvn_attention_bf16(const void* q, const void* k, const void* vt, void* out, 
               "mma: issue_qk(+waits) %lld  wait_p %lld  wait_v+issue_pv %lld  loop %lld\n",
               timing_buf[0] / nkv, timing_buf[1] / nkv, timing_buf[2] / nkv, timing_buf[3] / nkv, timing_buf[4] / nkv,
               timing_buf[8] / nkv, timing_buf[9] / nkv, timing_buf[10] / nkv, timing_buf[11] / nkv);
+    else if (impl == nullptr || atoi(impl) == 3)
+      fprintf(stderr, "[attn v3 timing, cycles per KV tile, thread 0] wait_s %lld  ldtm %lld  max+mailbox %lld  rescale %lld  exp %lld  "
+              "probe+wait_pv+store %lld\n", timing_buf[0] / nkv, timing_buf[1] / nkv, timing_buf[2] / nkv, timing_buf[5] / nkv,
+              timing_buf[3] / nkv, timing_buf[4] / nkv);
     else
       fprintf(stderr, "[attn v2 timing, cycles per KV tile] softmax wg0: wait_s %lld  ldtm %lld  max+rescale %lld  token_wait %lld  exp %lld  "
               "wait_pv+store %lld | mma: wait_v+wait_p0 %lld  pv0+wait_sfree0+qk0 %lld  wait_p1 %lld  pv1+qk1+loop %lld\n",

@@ -902,19 +902,33 @@ struct SoftmaxCtx3 {
   uint64_t *s_full, *s_free, *p_full, *pv_done;
   float* mail;      // [2][2][128]
   float m_ref, l;
-  int half, row, bar_id;
+  int half, row, bar_id, nkv;
+  bool s_ready;   // the previous tile's probe already saw S(j) complete
 };
 
+// The two barrier waits of a tile (S(j) complete, P buffer free) are almost always satisfied long before the thread
+// asks — but even a successful try_wait costs its ~100-300 clk round trip on the thread's critical path, twice per
+// tile.  Both are therefore PROBED early with the non-blocking test_wait (pv_done right after the scores are in
+// registers, s_full(j+1) before the P store), the result is consumed one phase later, and the blocking wait runs only
+// when a probe said "not yet".
 template <int POLY, bool MASKED>
-__device__ __forceinline__ void softmax_tile3(SoftmaxCtx3& c, int j, int valid) {
-  mbar_wait(c.s_full, j & 1);
+__device__ __forceinline__ void softmax_tile3(SoftmaxCtx3& c, int j, int valid, long long* tph, bool timing, long long& tprev) {
+#ifdef WVN_ATTN_TIMING
+#define WVN_TPH(i) if (timing) { const long long tn = clock64(); tph[i] += tn - tprev; tprev = tn; }
+#else
+#define WVN_TPH(i)
+#endif
+  if (!c.s_ready) mbar_wait(c.s_full, j & 1);
   tc_fence_after();
+  WVN_TPH(0)
   uint32_t sr[2][32];
   tmem_ld32(c.tmem_s, sr[0]);
   tmem_ld32(c.tmem_s + 32, sr[1]);
+  const bool pv_ok = j > 0 ? mbar_test_wait(c.pv_done, (j - 1) & 1) : true;   // probe: PV(j-1) retired?
   tmem_ld_wait();
   tc_fence_before();
   mbar_arrive(c.s_free);
+  WVN_TPH(1)
 
   float mx;
   if (!MASKED) {
@@ -940,6 +954,7 @@ __device__ __forceinline__ void softmax_tile3(SoftmaxCtx3& c, int j, int valid) 
   mb[c.half * 128 + c.row] = mx;
   named_bar_sync(c.bar_id, 64);
   mx = fmaxf(mx, mb[(c.half ^ 1) * 128 + c.row]);
+  WVN_TPH(2)
 
   bool waited_pv = false;
   if (j == 0) {
@@ -948,7 +963,7 @@ __device__ __forceinline__ void softmax_tile3(SoftmaxCtx3& c, int j, int valid) 
     const float m_new = fmaxf(c.m_ref, mx);
     const bool need = (m_new - c.m_ref) * c.sl2 > kRescaleThreshold;
     if (__any_sync(0xffffffffu, need)) {   // identical in both warps of the pair: `need` derives from the common max
-      mbar_wait(c.pv_done, (j - 1) & 1);
+      if (!pv_ok) mbar_wait(c.pv_done, (j - 1) & 1);
       waited_pv = true;
       tc_fence_after();
       const float alpha = need ? fast_exp2((c.m_ref - m_new) * c.sl2) : 1.f;
@@ -965,6 +980,7 @@ __device__ __forceinline__ void softmax_tile3(SoftmaxCtx3& c, int j, int valid) 
     }
   }
 
+  WVN_TPH(5)
   const float mb2 = c.m_ref * c.sl2;
   if (!MASKED) {
     const uint64_t sl2_2 = pack2(c.sl2, c.sl2), nmb2 = pack2(-mb2, -mb2);
@@ -1005,11 +1021,15 @@ __device__ __forceinline__ void softmax_tile3(SoftmaxCtx3& c, int j, int valid) 
       }
     }
   }
-  if (j > 0 && !waited_pv) mbar_wait(c.pv_done, (j - 1) & 1);
+  WVN_TPH(3)
+  c.s_ready = (j + 1 < c.nkv) ? mbar_test_wait(c.s_full, (j + 1) & 1) : false;   // probe: S(j+1) complete?
+  if (j > 0 && !waited_pv && !pv_ok) mbar_wait(c.pv_done, (j - 1) & 1);
   tmem_st32(c.tmem_p, sr[0]);
   tmem_st_wait();
   tc_fence_before();
   mbar_arrive(c.p_full);
+  WVN_TPH(4)
+#undef WVN_TPH
 }
 
 template <int POLY>
@@ -1150,9 +1170,23 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     c.mail = mail;
     c.m_ref = -INFINITY;
     c.l = 0.f;
+    c.nkv = nkv;
+    c.s_ready = false;
+#ifdef WVN_ATTN_TIMING
+    const bool timing = args.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+    long long tph[6] = {0, 0, 0, 0, 0, 0}, tprev = timing ? clock64() : 0;
+#else
+    constexpr bool timing = false;
+    long long* tph = nullptr;
+    long long tprev = 0;
+#endif
 #pragma unroll 1
-    for (int j = 0; j < nkv - 1; ++j) softmax_tile3<POLY, false>(c, j, kTileKV);
-    softmax_tile3<(POLY == 9 ? 9 : 0), true>(c, nkv - 1, args.n_valid - (nkv - 1) * kTileKV);
+    for (int j = 0; j < nkv - 1; ++j) softmax_tile3<POLY, false>(c, j, kTileKV, tph, timing, tprev);
+    softmax_tile3<(POLY == 9 ? 9 : 0), true>(c, nkv - 1, args.n_valid - (nkv - 1) * kTileKV, tph, timing, tprev);
+#ifdef WVN_ATTN_TIMING
+    if (timing)
+      for (int i = 0; i < 6; ++i) args.timing[i] = tph[i];
+#endif
 
     // ---- epilogue: combine the two halves' row sums, then O / l -> bf16 -> out[b, q, h*64 + 32*half + d]
     float* mb = c.mail + (nkv & 1) * 256;   // the buffer the last tile did not use
@@ -1187,379 +1221,6 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 }
 
 
-// =====================================================================================================================
-// v4 (round 2): v2's CTA (two query tiles per CTA, K / V^T fetched once per pair, one MMA issuer ordering both tiles,
-// exp phases alternating through the token barriers) with v3's TWO threads per query row.
-//
-// Round-2 phase timing of v2 (after the elect_one fix of the issue loops): a softmax warpgroup spends ~1500 clk of its
-// ~2700 clk period in the exp phase although the phase needs only 768 clk of the sub-partition's MUFU pipe — one warp
-// per sub-partition cannot ISSUE the ~600 instructions of its 128-element rows any faster (IPC ~0.4: dependent FFMA2 /
-// MUFU / F2FP chains).  With the row split over two threads the exp phase of a query tile is carried by two warps per
-// sub-partition (64 elements per thread), i.e. twice the issue capacity while the token still keeps the other query
-// tile's warps out of the MUFU pipe; the MUFU-free phases (tcgen05.ld, max, P store) halve per thread as well.
-//   warps  0-7  : softmax of query tile 0 (warps 0-3: score columns [0,64), warps 4-7: [64,128); 32 O columns each)
-//   warps  8-15 : softmax of query tile 1
-//   warp   16   : TMA producer      warp 17 : MMA issuer      warps 18-19 : idle (they complete the aux warpgroup)
-// =====================================================================================================================
-namespace v4 {
-constexpr int kThreads = 640;
-constexpr int kRegsAux = 24, kRegsSoftmax = 112;   // per sub-partition: 24 + 4 * 112 = 472 <= 5 * 96 (launch allocation)
-constexpr int kWarpTma = 16, kWarpMma = 17;
-constexpr uint32_t kOffMail = v2::kOffBar + 256;    // [2 tiles][2 buffers][2 halves][128 rows] fp32 row-max mailbox
-constexpr uint32_t kSmemBytes = kOffMail + 2 * 2 * 2 * 128 * 4;
-constexpr int kBarPair0 = 1;                        // named barriers 1..8: (tile, lane quarter) pairs, 64 threads
-constexpr int kBarTok0 = 9, kBarTok1 = 10;          // "query tile 0 / 1 may start its exp phase", 512 threads
-}  // namespace v4
-
-struct SoftmaxCtx4 {
-  uint32_t tmem_s, tmem_o, tmem_p;
-  float sl2;
-  uint64_t *s_full, *s_free, *p_full, *pv_done;
-  float* mail;      // this tile's [2][2][128]
-  float m_ref, l;
-  int half, row, bar_id, wg, nkv;
-  bool paired;
-};
-
-template <int POLY, bool MASKED>
-__device__ __forceinline__ void softmax_tile4(SoftmaxCtx4& c, int j, int valid) {
-  mbar_wait(c.s_full, j & 1);
-  tc_fence_after();
-  uint32_t sr[2][32];
-  tmem_ld32(c.tmem_s, sr[0]);
-  tmem_ld32(c.tmem_s + 32, sr[1]);
-  tmem_ld_wait();
-  tc_fence_before();
-  mbar_arrive(c.s_free);
-
-  float mx;
-  if (!MASKED) {
-    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      m0 = max3(m0, __uint_as_float(sr[0][i]), __uint_as_float(sr[0][i + 1]));
-      m1 = max3(m1, __uint_as_float(sr[0][i + 2]), __uint_as_float(sr[0][i + 3]));
-      m2 = max3(m2, __uint_as_float(sr[1][i]), __uint_as_float(sr[1][i + 1]));
-      m3 = max3(m3, __uint_as_float(sr[1][i + 2]), __uint_as_float(sr[1][i + 3]));
-    }
-    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-  } else {
-    mx = -INFINITY;
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        mx = fmaxf(mx, (c.half * 64 + q * 32 + i < valid) ? __uint_as_float(sr[q][i]) : -INFINITY);
-  }
-  float* mb = c.mail + (j & 1) * 256;
-  mb[c.half * 128 + c.row] = mx;
-  named_bar_sync(c.bar_id, 64);
-  mx = fmaxf(mx, mb[(c.half ^ 1) * 128 + c.row]);
-
-  bool waited_pv = false;
-  if (j == 0) {
-    c.m_ref = mx;
-  } else {
-    const float m_new = fmaxf(c.m_ref, mx);
-    const bool need = (m_new - c.m_ref) * c.sl2 > kRescaleThreshold;
-    if (__any_sync(0xffffffffu, need)) {
-      mbar_wait(c.pv_done, (j - 1) & 1);
-      waited_pv = true;
-      tc_fence_after();
-      const float alpha = need ? fast_exp2((c.m_ref - m_new) * c.sl2) : 1.f;
-      if (need) c.m_ref = m_new;
-      c.l *= alpha;
-      uint32_t r[32];
-      tmem_ld32(c.tmem_o, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-      tmem_st32(c.tmem_o, r);
-      tmem_st_wait();
-      tc_fence_before();
-    }
-  }
-
-  // ---- exp phase: owned by one query tile's warps at a time
-  if (c.paired && (c.wg == 1 || j > 0)) named_bar_sync(c.wg ? v4::kBarTok1 : v4::kBarTok0, 512);
-  const float mb2 = c.m_ref * c.sl2;
-  if (!MASKED) {
-    const uint64_t sl2_2 = pack2(c.sl2, c.sl2), nmb2 = pack2(-mb2, -mb2);
-    uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const uint64_t x2 = fma2(pack2(__uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1])), sl2_2, nmb2);
-        float e0, e1;
-        if (POLY == 9) {
-          unpack2(x2, e0, e1);
-        } else if (((i >> 1) & 7) < POLY) {
-          poly_exp2_pair(x2, e0, e1);
-        } else {
-          float x0, x1;
-          unpack2(x2, x0, x1);
-          e0 = fast_exp2(x0);
-          e1 = fast_exp2(x1);
-        }
-        if ((i >> 1) & 1) lb = add2(lb, pack2(e0, e1)); else la = add2(la, pack2(e0, e1));
-        sr[0][q * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
-      }
-    }
-    float s0, s1;
-    unpack2(add2(la, lb), s0, s1);
-    c.l += s0 + s1;
-  } else {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const int col = c.half * 64 + q * 32 + i;
-        const float e0 = (col < valid) ? fast_exp2(fmaf(__uint_as_float(sr[q][i]), c.sl2, -mb2)) : 0.f;
-        const float e1 = (col + 1 < valid) ? fast_exp2(fmaf(__uint_as_float(sr[q][i + 1]), c.sl2, -mb2)) : 0.f;
-        c.l += e0 + e1;
-        sr[0][q * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
-      }
-    }
-  }
-  if (c.paired && (c.wg == 0 || j + 1 < c.nkv)) named_bar_arrive(c.wg ? v4::kBarTok0 : v4::kBarTok1, 512);
-
-  if (j > 0 && !waited_pv) mbar_wait(c.pv_done, (j - 1) & 1);
-  tmem_st32(c.tmem_p, sr[0]);
-  tmem_st_wait();
-  tc_fence_before();
-  mbar_arrive(c.p_full);
-}
-
-template <int POLY>
-__global__ void __launch_bounds__(v4::kThreads, 1)
-attention4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                  const __grid_constant__ CUtensorMap tmap_vt, const AttnArgs args) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + v2::kOffBar);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = k_full + v2::kStages;
-  uint64_t* v_full = k_empty + v2::kStages;
-  uint64_t* v_empty = v_full + v2::kStages;
-  uint64_t* s_full = v_empty + v2::kStages;        // [2]
-  uint64_t* s_free = s_full + 2;                   // [2]
-  uint64_t* p_full = s_full + 4;                   // [2]
-  uint64_t* pv_done = s_full + 6;                  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
-  float* mail = reinterpret_cast<float*>(smem + v4::kOffMail);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int ntiles = args.npad / kTileQ;
-  const int qpair = args.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
-  const int bh = args.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
-  const int q_tile0 = 2 * qpair;
-  const bool has1 = q_tile0 + 1 < ntiles;
-  const int nkv = ntiles;
-
-  if (warp == v4::kWarpMma && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < v2::kStages; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-    }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&s_free[t], 256);
-      mbar_init(&p_full[t], 256);
-      mbar_init(&pv_done[t], 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == v4::kWarpTma) tmem_alloc(tmem_slot, v2::kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == v4::kWarpTma) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(v4::kRegsAux));
-    const int row0 = bh * args.npad;
-    if (elect_one_sync()) {
-      tma_prefetch_desc(&tmap_q);
-      tma_prefetch_desc(&tmap_k);
-      tma_prefetch_desc(&tmap_vt);
-      mbar_arrive_expect_tx(q_full, has1 ? 2 * kQBytes : kQBytes);
-      tma_load_2d(&tmap_q, q_full, smem + v2::kOffQ, 0, row0 + q_tile0 * kTileQ);
-      if (has1) tma_load_2d(&tmap_q, q_full, smem + v2::kOffQ + kQBytes, 0, row0 + (q_tile0 + 1) * kTileQ);
-    }
-    __syncwarp();
-    for (int j = 0; j < nkv; ++j) {
-      const int st = j % v2::kStages;
-      const uint32_t ph = (j / v2::kStages) & 1;
-      mbar_wait(&k_empty[st], ph ^ 1);
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&k_full[st], kKBytes);
-        tma_load_2d(&tmap_k, &k_full[st], smem + v2::kOffK + st * kKBytes, 0, row0 + j * kTileKV);
-      }
-      __syncwarp();
-      mbar_wait(&v_empty[st], ph ^ 1);
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&v_full[st], kVBytes);
-        tma_load_2d(&tmap_vt, &v_full[st], smem + v2::kOffV + st * kVBytes, j * kTileKV, bh * kDh);
-        tma_load_2d(&tmap_vt, &v_full[st], smem + v2::kOffV + st * kVBytes + kVBytes / 2, j * kTileKV + 64, bh * kDh);
-      }
-      __syncwarp();
-    }
-  } else if (warp == v4::kWarpMma) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(v4::kRegsAux));
-    constexpr uint32_t idesc_s = make_idesc_bf16(kTileQ, kTileKV);
-    constexpr uint32_t idesc_o = make_idesc_bf16(kTileQ, kDh);
-    auto qk = [&](int t, int j) {
-      const uint64_t desc_q = make_sw128_kmajor_desc(smem_u32(smem + v2::kOffQ + t * kQBytes));
-      const uint64_t desc_k = make_sw128_kmajor_desc(smem_u32(smem + v2::kOffK + (j % v2::kStages) * kKBytes));
-      const uint32_t tmem_s = tmem_base + t * v2::kTileCols + kColS;
-#pragma unroll
-      for (int k = 0; k < kDh / 16; ++k) umma_bf16_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc_s, k != 0);
-      umma_commit(&s_full[t]);
-    };
-    auto pv = [&](int t, int j) {
-      const uint32_t v_addr = smem_u32(smem + v2::kOffV + (j % v2::kStages) * kVBytes);
-      const uint32_t tmem_o = tmem_base + t * v2::kTileCols + kColO;
-      const uint32_t tmem_p = tmem_base + t * v2::kTileCols + kColP;
-#pragma unroll
-      for (int ks = 0; ks < kTileKV / 16; ++ks) {
-        const uint64_t desc_v = make_sw128_kmajor_desc(v_addr + (ks >> 2) * (kVBytes / 2)) + 2 * (ks & 3);
-        umma_bf16_ts(tmem_o, tmem_p + 8 * ks, desc_v, idesc_o, (j | ks) != 0);
-      }
-      umma_commit(&pv_done[t]);
-    };
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    if (elect_one_sync()) {
-      qk(0, 0);
-      if (has1) qk(1, 0);
-      umma_commit(&k_empty[0]);
-    }
-    __syncwarp();
-    if (nkv > 1) {
-      mbar_wait(&k_full[1 % v2::kStages], 0);
-      mbar_wait(&s_free[0], 0);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        qk(0, 1);
-        if (!has1) umma_commit(&k_empty[1 % v2::kStages]);
-      }
-      __syncwarp();
-      if (has1) {
-        mbar_wait(&s_free[1], 0);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          qk(1, 1);
-          umma_commit(&k_empty[1 % v2::kStages]);
-        }
-        __syncwarp();
-      }
-    }
-    for (int j = 0; j < nkv; ++j) {
-      const int st = j % v2::kStages;
-      const uint32_t ph = (j / v2::kStages) & 1;
-      const int st2 = (j + 2) % v2::kStages;
-      const uint32_t ph2 = ((j + 2) / v2::kStages) & 1;
-      mbar_wait(&v_full[st], ph);
-      mbar_wait(&p_full[0], j & 1);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        pv(0, j);
-        if (!has1) umma_commit(&v_empty[st]);
-      }
-      __syncwarp();
-      if (j + 2 < nkv) {
-        mbar_wait(&k_full[st2], ph2);
-        mbar_wait(&s_free[0], (j + 1) & 1);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          qk(0, j + 2);
-          if (!has1) umma_commit(&k_empty[st2]);
-        }
-        __syncwarp();
-      }
-      if (has1) {
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          pv(1, j);
-          umma_commit(&v_empty[st]);
-        }
-        __syncwarp();
-        if (j + 2 < nkv) {
-          mbar_wait(&s_free[1], (j + 1) & 1);
-          tc_fence_after();
-          if (elect_one_sync()) {
-            qk(1, j + 2);
-            umma_commit(&k_empty[st2]);
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(v4::kRegsAux));
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(v4::kRegsSoftmax));
-    const int wg = warp >> 3;
-    if (wg == 0 || has1) {
-      const int quarter = warp & 3;
-      const int half = (warp >> 2) & 1;
-      const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-      SoftmaxCtx4 c;
-      c.half = half;
-      c.row = quarter * 32 + lane;
-      c.bar_id = v4::kBarPair0 + wg * 4 + quarter;
-      c.wg = wg; c.nkv = nkv; c.paired = has1 && !args.no_token;
-      c.tmem_s = tmem_base + lane_base + wg * v2::kTileCols + kColS + half * 64;
-      c.tmem_o = tmem_base + lane_base + wg * v2::kTileCols + kColO + half * 32;
-      c.tmem_p = tmem_base + lane_base + wg * v2::kTileCols + kColP + half * 32;
-      c.sl2 = args.scale_log2;
-      c.s_full = &s_full[wg]; c.s_free = &s_free[wg]; c.p_full = &p_full[wg]; c.pv_done = &pv_done[wg];
-      c.mail = mail + wg * 512;
-      c.m_ref = -INFINITY;
-      c.l = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < nkv - 1; ++j) softmax_tile4<POLY, false>(c, j, kTileKV);
-      softmax_tile4<(POLY == 9 ? 9 : 0), true>(c, nkv - 1, args.n_valid - (nkv - 1) * kTileKV);
-
-      float* mb = c.mail + (nkv & 1) * 256;
-      mb[half * 128 + c.row] = c.l;
-      named_bar_sync(c.bar_id, 64);
-      const float inv_l = 1.f / (c.l + mb[(half ^ 1) * 128 + c.row]);
-      mbar_wait(c.pv_done, (nkv - 1) & 1);
-      tc_fence_after();
-      const int b = bh / args.heads;
-      const int h = bh - b * args.heads;
-      const long long q_idx = static_cast<long long>(b) * args.npad + (q_tile0 + wg) * kTileQ + c.row;
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + q_idx * args.ldo + h * kDh + half * 32;
-      uint32_t r[32];
-      tmem_ld32(c.tmem_o, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        float f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[8 * t + i]) * inv_l;
-        st_global_v4(dst + 8 * t, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                     pack_bf16x2(f[6], f[7]));
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == v4::kWarpTma) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, v2::kTmemCols);
-  }
-}
-
 }  // namespace
 
 int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* vt, cudaStream_t stream) {
@@ -1579,13 +1240,14 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
     poly = e ? atoi(e) : kDefaultPoly;
     if ((poly < 0 || poly > 4) && poly != 9) poly = kDefaultPoly;
   }
-  // $WVN_ATTN_IMPL: 2 (default) = one CTA per SM owning two query tiles with ordered softmax warpgroups;
-  // 1 = round 1's kernel (one query tile per CTA, 2 independent CTAs per SM), kept for A/B measurements
+  // $WVN_ATTN_IMPL: 3 (default) = one query tile per CTA, 2 CTAs per SM, two threads per query row;
+  // 1 = the same with one thread per row (round 1's structure); 2 = one CTA per SM owning two query tiles with ordered
+  // softmax warpgroups.  All three are parity-tested; measured on B200 (B = 32, stand-alone): 766 / 750 / 720 TFLOP/s
   static int impl = -1;
   if (impl < 0) {
     const char* e = getenv("WVN_ATTN_IMPL");
-    impl = e ? atoi(e) : 2;
-    if (impl < 1 || impl > 4) impl = 2;
+    impl = e ? atoi(e) : 3;
+    if (impl < 1 || impl > 3) impl = 3;
   }
   static int no_token = -1;  // $WVN_ATTN_TOKEN=0: let the two softmax warpgroups free-run (A/B of the exp-phase ordering)
   if (no_token < 0) {
@@ -1595,10 +1257,9 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
   AttnArgs a2 = a;
   a2.no_token = no_token;
   const int ntiles = a.npad / kTileQ;
-  dim3 grid((impl == 2 || impl == 4) ? (ntiles + 1) / 2 : ntiles, static_cast<unsigned>(bh));
-  const int threads = impl == 2 ? v2::kThreads : (impl == 3 ? v3::kThreads : (impl == 4 ? v4::kThreads : kThreads));
-  const uint32_t smem_bytes =
-      impl == 2 ? v2::kSmemBytes : (impl == 3 ? v3::kSmemBytes : (impl == 4 ? v4::kSmemBytes : kSmemBytes));
+  dim3 grid(impl == 2 ? (ntiles + 1) / 2 : ntiles, static_cast<unsigned>(bh));
+  const int threads = impl == 2 ? v2::kThreads : (impl == 3 ? v3::kThreads : kThreads);
+  const uint32_t smem_bytes = impl == 2 ? v2::kSmemBytes : (impl == 3 ? v3::kSmemBytes : kSmemBytes);
   auto launch = [&](auto kern) -> int {
     WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     prof_begin(PROF_ATTENTION, stream);
@@ -1614,15 +1275,6 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
       case 3: WVN_PROPAGATE(launch(attention2_kernel<3>)); break;
       case 4: WVN_PROPAGATE(launch(attention2_kernel<4>)); break;
       default: WVN_PROPAGATE(launch(attention2_kernel<9>)); break;
-    }
-  } else if (impl == 4) {
-    switch (poly) {
-      case 0: WVN_PROPAGATE(launch(attention4_kernel<0>)); break;
-      case 1: WVN_PROPAGATE(launch(attention4_kernel<1>)); break;
-      case 2: WVN_PROPAGATE(launch(attention4_kernel<2>)); break;
-      case 3: WVN_PROPAGATE(launch(attention4_kernel<3>)); break;
-      case 4: WVN_PROPAGATE(launch(attention4_kernel<4>)); break;
-      default: WVN_PROPAGATE(launch(attention4_kernel<9>)); break;
     }
   } else if (impl == 3) {
     switch (poly) {

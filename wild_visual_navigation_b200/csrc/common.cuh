@@ -101,6 +101,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Non-blocking probe (mbarrier.test_wait returns at once; its result latency can hide behind independent work).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // Bounded wait: a protocol bug must surface as a trapped kernel (an error code on the
 // host), never as a hung GPU.  ~4e9 SM cycles ≈ 2 s at boost clocks.
 #ifndef WVN_MBAR_TIMEOUT_CYCLES
