@@ -197,6 +197,20 @@ int wvn_segment_relabel(long long* seg, int batch, long long pix_per_frame, int 
 int wvn_supervision_pool(const long long* seg, const float* mask, int batch, int channels, int h, int w, int smax,
                          float* y, unsigned char* y_valid, float* count_ws, void* stream);
 
+/* Footprint projection + rasterisation — replaces ImageProjector.project_and_render
+ * (image_projector/image_projector.py:152-197; its kornia calls transform_points, PinholeCamera.project and
+ * draw_convex_polygon are restated, see oracle/image_projector.py) and, when supervision_inout != NULL, the mask update of
+ * TraversabilityEstimator.add_supervision_node (traversability_estimator/traversability_estimator.py:281-284):
+ *   supervision = fmin(supervision, mask * traversability).
+ * K: [batch,4,4] SCALED camera matrices (ImageProjector.__init__ :61-75); pose_camera_in_world: [batch,4,4];
+ * points: [batch,n_points,3] convex polygon in the world frame; colors: [batch,3] (color_batched) or [3];
+ * traversability: device scalar or NULL (= 1).  Outputs (each may be NULL): masks [batch,3,h,w] fp32 with NaN outside the
+ * polygon (and where the colour is 0, as `masks[masks == 0] = nan`); projected [batch,n_points,2] pixel coordinates
+ * (NaN for points behind the camera); valid [batch,n_points] uint8 (check_validity :103-124). */
+int wvn_project_and_render(const float* K, const float* pose_camera_in_world, const float* points, const float* colors,
+                           int color_batched, int batch, int n_points, int h, int w, const float* traversability,
+                           float* masks, float* projected, unsigned char* valid, float* supervision_inout, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Traversability MLP inference over every pixel — replaces
  *   x = dense_feat[0].permute(1,2,0).reshape(-1, D); prediction = model.forward(Data(x));

@@ -55,6 +55,8 @@ def resize_image(img: torch.Tensor, new_h: int) -> torch.Tensor:
     """``ImageProjector.resize_image`` for the square configuration (image_projector.py:55-59,199-200):
     ``T.Compose([T.Resize(new_h, NEAREST), T.CenterCrop(new_h)])`` on a (B,3,H,W) tensor."""
     B, C, H, W = img.shape
+    if isinstance(new_h, (tuple, list)):   # T.Resize([new_h, new_w], NEAREST): the non-square configuration, no crop
+        return F.interpolate(img, size=tuple(new_h), mode="nearest")
     rh, rw = resized_size(H, W, new_h)
     if (rh, rw) != (H, W):
         img = F.interpolate(img, size=(rh, rw), mode="nearest")

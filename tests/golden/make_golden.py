@@ -171,6 +171,71 @@ def make_supervision():
                os.path.join(HERE, "supervision.pt"))
 
 
+def make_image_projector():
+    """Runs the reference's OWN ``ImageProjector`` (image_projector/image_projector.py:16-200: scaled camera matrix,
+    project / check_validity, project_and_render, resize_image) and ``make_polygon_from_points`` (utils/meshes.py:156-165).
+    kornia / liegroups / pytictac are absent here, so the three kornia routines the class calls are provided by the
+    oracle's restatement (oracle/image_projector.py, [EXTERNAL-RECALLED]) through stub modules: the golden pins the
+    reference's in-repo logic; the kornia part stays unpinned against kornia itself."""
+    import importlib.util
+    from oracle import image_projector as oip
+
+    class _PinholeCamera:
+        def __init__(self, intrinsics, extrinsics, height, width):
+            self.intrinsics, self.extrinsics, self.height, self.width = intrinsics, extrinsics, height, width
+
+        batch_size = property(lambda self: self.intrinsics.shape[0])
+        camera_matrix = property(lambda self: self.intrinsics[..., :3, :3])
+
+        def project(self, point_3d):
+            P = self.intrinsics @ self.extrinsics
+            return oip.convert_points_from_homogeneous(oip.transform_points(P, point_3d))
+
+    def _mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    names = ["pytictac", "kornia", "kornia.geometry", "kornia.geometry.camera", "kornia.geometry.camera.pinhole",
+             "kornia.geometry.linalg", "kornia.utils", "kornia.utils.draw", "liegroups", "liegroups.torch"]
+    _mod("pytictac", Timer=object)
+    for n in names[1:]:
+        _mod(n)
+    sys.modules["kornia.geometry.camera.pinhole"].PinholeCamera = _PinholeCamera
+    sys.modules["kornia.geometry.linalg"].transform_points = oip.transform_points
+    sys.modules["kornia.utils.draw"].draw_convex_polygon = oip.draw_convex_polygon
+    sys.modules["liegroups.torch"].SE3 = sys.modules["liegroups.torch"].SO3 = object
+    spec = importlib.util.spec_from_file_location(
+        "ref_image_projector", os.path.join(ref_import.REF_ROOT, "wild_visual_navigation/image_projector/image_projector.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    spec = importlib.util.spec_from_file_location(
+        "ref_meshes", os.path.join(ref_import.REF_ROOT, "wild_visual_navigation/utils/meshes.py"))
+    meshes = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(meshes)
+
+    B = 7
+    K, poses, fp = oip.synthetic_footprints(B, seed=3, image=48)
+    K[:, 0, 0] *= 1.1            # fx != fy: the square-crop branch of the constructor overwrites fx with fy * s
+    K[:, 0, 2] += 12             # 48 x 72 camera, principal point off-centre
+    corners = torch.tensor([[0.4, 0.3, 0.0], [0.4, -0.3, 0.0], [1.3, -0.35, 0.0], [1.3, 0.25, 0.0]])
+    poly_ref = meshes.make_polygon_from_points(corners, grid_size=10)
+    out = {"K": K, "poses": poses, "corners": corners, "polygon": poly_ref, "h": 48, "w": 72}
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(2, 3, 48, 72, generator=g)
+    for tag, kw in (("square", dict(new_h=32)), ("rect", dict(new_h=24, new_w=40)), ("native", dict())):
+        im = mod.ImageProjector(K.clone(), torch.tensor(48), torch.tensor(72), **kw)
+        colors = torch.tensor([0.0, 1.0, 0.5]) if tag == "rect" else torch.ones(3)
+        masks, _, proj, valid = im.project_and_render(poses.clone(), fp.clone(), colors)
+        out[tag] = {"kw": kw, "sK": im.camera.intrinsics.clone(), "colors": colors, "masks": masks.clone(),
+                    "projected": proj.clone(), "valid": valid.clone(), "resized": im.resize_image(img)}
+    out["img"] = img
+    torch.save(out, os.path.join(HERE, "image_projector.pt"))
+    for n in names:
+        sys.modules.pop(n, None)
+
+
 def _reference_method(rel_path, name):
     """A method of a reference class whose module cannot be imported here: its source is read from the reference file
     with ``ast`` and compiled as a free function (nothing is copied into this repository)."""
@@ -410,6 +475,7 @@ if __name__ == "__main__":
     make_handoff(ns)
     make_checkpoint(ns)
     make_supervision()
+    make_image_projector()
     make_sparsify()
     make_segments(ns)
     make_dino_wrapper()

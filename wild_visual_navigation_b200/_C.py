@@ -64,6 +64,7 @@ SIGNATURES = {
     "wvn_segment_reduce": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
     "wvn_segment_relabel": (_I, [_P, _I, _L, _I, _P, _P, _P]),
     "wvn_supervision_pool": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "wvn_project_and_render": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "wvn_mlp_infer_create": (_I, [_I, _I, _I, _I, POINTER(_P)]),
     "wvn_mlp_infer_destroy": (None, [_P]),
     "wvn_mlp_infer_reserve": (_I, [_P, _I]),

@@ -19,5 +19,6 @@ from .feature_extractor import (  # noqa: E402,F401
     FeatureExtractor,
 )
 from .traversability_estimator import TraversabilityEstimator  # noqa: E402,F401
+from .image_projector import ImageProjector  # noqa: E402,F401
 from .inference import TraversabilityInference  # noqa: E402,F401
 from .hot_path import HotPathStep  # noqa: E402,F401

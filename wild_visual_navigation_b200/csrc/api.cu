@@ -17,6 +17,7 @@
 #include "mlp_train_fused.h"
 #include "pixel_head.h"
 #include "segment_kernels.h"
+#include "footprint_kernels.h"
 #include "stego_kmeans.h"
 #include "vit_kernels.h"
 
@@ -606,6 +607,17 @@ int wvn_supervision_pool(const long long* seg, const float* mask, int batch, int
                          float* y, unsigned char* y_valid, float* count_ws, void* stream) {
   WVN_REQUIRE(seg && mask && y && y_valid && count_ws, "wvn_supervision_pool: null argument");
   return supervision_pool(seg, mask, batch, channels, h, w, smax, y, y_valid, count_ws, S(stream));
+}
+
+int wvn_project_and_render(const float* K, const float* pose_camera_in_world, const float* points, const float* colors,
+                           int color_batched, int batch, int n_points, int h, int w, const float* traversability,
+                           float* masks, float* projected, unsigned char* valid, float* supervision_inout, void* stream) {
+  WVN_REQUIRE(K && pose_camera_in_world && points, "wvn_project_and_render: null argument");
+  WVN_REQUIRE(colors || (!masks && !supervision_inout), "wvn_project_and_render: colors are required to render");
+  FootprintArgs a;
+  a.batch = batch; a.n_points = n_points; a.h = h; a.w = w; a.color_batched = color_batched;
+  return footprint_render(a, K, pose_camera_in_world, points, colors, traversability, masks, projected, valid,
+                          supervision_inout, S(stream));
 }
 
 }  // extern "C"

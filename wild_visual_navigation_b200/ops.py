@@ -128,6 +128,32 @@ def pool_supervision(seg: torch.Tensor, mask: torch.Tensor, smax: int):
     return y, valid.bool()
 
 
+def project_and_render(sK, pose_camera_in_world, points, colors, h, w, render=True, supervision=None, traversability=None):
+    """Footprint projection + rasterisation (ImageProjector.project_and_render, image_projector.py:152-197).
+    sK (B,4,4) scaled camera matrices, pose (B,4,4), points (B,N,3), colors (B,3) | (3,) | None.
+    -> (masks (B,3,h,w) or None, projected (B,N,2), valid (B,N) bool); ``supervision`` (B,3,h,w) is updated in place
+    with fmin(supervision, mask * traversability) (traversability_estimator.py:281-284)."""
+    _C.require_device()
+    B, N = points.shape[0], points.shape[1]
+    dev = points.device
+    sK, pose, points = sK.float().contiguous(), pose_camera_in_world.float().contiguous(), points.float().contiguous()
+    assert sK.shape == (B, 4, 4) and pose.shape == (B, 4, 4) and points.shape == (B, N, 3)
+    if colors is not None:
+        colors = colors.to(dev, torch.float32).contiguous()
+        assert colors.shape in ((3,), (B, 3))
+    masks = torch.empty(B, 3, h, w, device=dev, dtype=torch.float32) if render else None
+    proj = torch.empty(B, N, 2, device=dev, dtype=torch.float32)
+    valid = torch.empty(B, N, device=dev, dtype=torch.uint8)
+    if supervision is not None:
+        assert supervision.shape == (B, 3, h, w) and supervision.dtype == torch.float32 and supervision.is_contiguous()
+    if traversability is not None:
+        traversability = traversability.to(dev, torch.float32).reshape(-1)[:1].contiguous()
+    check(lib().wvn_project_and_render(ptr(sK), ptr(pose), ptr(points), ptr(colors),
+                                       int(colors is not None and colors.dim() == 2), B, N, h, w, ptr(traversability),
+                                       ptr(masks), ptr(proj), ptr(valid), ptr(supervision), stream()))
+    return masks, proj, valid.bool()
+
+
 def stego_kmeans(head, batch, npad, patches, code_col, code_dim, logit_col, k, iters, centroids_out=None):
     """Per-image k-means of the code columns of the head output ``head`` [batch*npad, ld]; leaves the per-patch
     nearest-centroid scores in columns [logit_col, logit_col + k) (see include/wvn_b200.h)."""
