@@ -197,6 +197,18 @@ int wvn_segment_relabel(long long* seg, int batch, long long pix_per_frame, int 
 int wvn_supervision_pool(const long long* seg, const float* mask, int batch, int channels, int h, int w, int smax,
                          float* y, unsigned char* y_valid, float* count_ws, void* stream);
 
+/* SLIC superpixels — replaces fast_slic's Slic(num_components, compactness).iterate(np.uint8(img * 255)) behind
+ * FeatureExtractor(segmentation_type="slic") (feature_extractor/feature_extractor.py:88-95, 221-225).  fast-slic is an
+ * un-vendored C++ dependency; the algorithm is restated in all-integer form (oracle/slic.py is the definition; the labels
+ * of this kernel are bit-identical to it).  img: [batch,3,h,w] fp32 in [0,1]; labels: [batch,h,w] int64 cluster ids in
+ * [0, nx*ny) (empty clusters are possible: compact with wvn_segment_relabel); lut_*: device copies of the host tables
+ * wvn_slic_tables() fills (256 / 9 / 4096 ints); workspace: wvn_slic_workspace_bytes(). */
+void wvn_slic_tables(int* g256, int* m9, int* f4096);
+int wvn_slic_geometry(int h, int w, int num_components, int* grid_interval, int* nx, int* ny);
+size_t wvn_slic_workspace_bytes(int batch, int h, int w, int num_components);
+int wvn_slic(const float* img, int batch, int h, int w, int num_components, float compactness, int iters,
+             const int* lut_g, const int* lut_m, const int* lut_f, long long* labels, void* workspace, void* stream);
+
 /* Footprint projection + rasterisation — replaces ImageProjector.project_and_render
  * (image_projector/image_projector.py:152-197; its kornia calls transform_points, PinholeCamera.project and
  * draw_convex_polygon are restated, see oracle/image_projector.py) and, when supervision_inout != NULL, the mask update of

@@ -64,6 +64,10 @@ SIGNATURES = {
     "wvn_segment_reduce": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
     "wvn_segment_relabel": (_I, [_P, _I, _L, _I, _P, _P, _P]),
     "wvn_supervision_pool": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "wvn_slic_tables": (None, [_P, _P, _P]),
+    "wvn_slic_geometry": (_I, [_I, _I, _I, _P, _P, _P]),
+    "wvn_slic_workspace_bytes": (_S, [_I, _I, _I, _I]),
+    "wvn_slic": (_I, [_P, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P]),
     "wvn_project_and_render": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "wvn_mlp_infer_create": (_I, [_I, _I, _I, _I, POINTER(_P)]),
     "wvn_mlp_infer_destroy": (None, [_P]),

@@ -18,6 +18,7 @@
 #include "pixel_head.h"
 #include "segment_kernels.h"
 #include "footprint_kernels.h"
+#include "slic_kernels.h"
 #include "stego_kmeans.h"
 #include "vit_kernels.h"
 
@@ -607,6 +608,25 @@ int wvn_supervision_pool(const long long* seg, const float* mask, int batch, int
                          float* y, unsigned char* y_valid, float* count_ws, void* stream) {
   WVN_REQUIRE(seg && mask && y && y_valid && count_ws, "wvn_supervision_pool: null argument");
   return supervision_pool(seg, mask, batch, channels, h, w, smax, y, y_valid, count_ws, S(stream));
+}
+
+void wvn_slic_tables(int* g256, int* m9, int* f4096) { slic_tables(g256, m9, f4096); }
+
+int wvn_slic_geometry(int h, int w, int num_components, int* grid_interval, int* nx, int* ny) {
+  WVN_REQUIRE(h > 0 && w > 0 && num_components > 0 && grid_interval && nx && ny, "wvn_slic_geometry: bad argument");
+  slic_geometry(h, w, num_components, grid_interval, nx, ny);
+  return WVN_OK;
+}
+
+size_t wvn_slic_workspace_bytes(int batch, int h, int w, int num_components) {
+  return slic_workspace_bytes(batch, h, w, num_components);
+}
+
+int wvn_slic(const float* img, int batch, int h, int w, int num_components, float compactness, int iters,
+             const int* lut_g, const int* lut_m, const int* lut_f, long long* labels, void* workspace, void* stream) {
+  WVN_REQUIRE(img && lut_g && lut_m && lut_f && labels && workspace, "wvn_slic: null argument");
+  return slic_segment(img, batch, h, w, num_components, compactness, iters, lut_g, lut_m, lut_f, labels, workspace,
+                      S(stream));
 }
 
 int wvn_project_and_render(const float* K, const float* pose_camera_in_world, const float* points, const float* colors,

@@ -8,9 +8,10 @@
   * adjacency + centroids come from the same pass (no per-segment Python loops / host syncs);
   * when segmentation and features are both "stego"/"dino" on the same backbone, one ViT forward
     serves both (the reference runs two backbones).
-Supported on the hot path: segmentation_type in {"stego", "grid", "random", "none"/None},
-feature_type in {"dino", "stego"}.  "slic" (fast_slic), "sift", "torchvision", "histogram" are
-out of scope and raise.
+Supported: segmentation_type in {"slic" (the constructor default), "stego", "grid", "random", "none"/None},
+feature_type in {"dino", "stego"}.  "slic" is an all-integer SLIC kernel (csrc/slic_kernels.cu; fast_slic itself is an
+un-vendored C++ package, see oracle/slic.py for what is and is not restated).  "sift", "torchvision", "histogram"
+features are out of scope and raise.
 """
 from __future__ import annotations
 
@@ -30,8 +31,12 @@ class FeatureExtractor:
         self._feature_type = feature_type
         self._input_size = input_size
         self.segment_extractor = SegmentExtractor()
-        if segmentation_type not in ("stego", "grid", "random", "none", None):
-            raise ValueError(f"segmentation_type [{segmentation_type}] is outside the B200 hot path")
+        if segmentation_type not in ("slic", "stego", "grid", "random", "none", None):
+            raise ValueError(f"segmentation_type [{segmentation_type}] not supported")
+        # fast_slic.Slic(num_components, compactness) of the reference (feature_extractor.py:88-95)
+        self._slic_num_components = kwargs.get("slic_num_components", 100)
+        self._slic_compactness = kwargs.get("slic_compactness", 10)
+        self._slic_iters = kwargs.get("slic_iters", 10)
         common = dict(backbone_type=kwargs.get("backbone_type", "vit_small"), patch_size=kwargs.get("patch_size", 8),
                       max_batch=kwargs.get("max_batch", 1), chunk=kwargs.get("chunk", 0))
         need_stego = feature_type == "stego" or segmentation_type == "stego"
@@ -88,12 +93,17 @@ class FeatureExtractor:
         B, _, H, W = img.shape
         assert B == 1, "extract() keeps the reference's single-frame contract; use extract_batch() for B > 1"
         r = self.extract_batch(img, **kwargs)
-        n = int(r["n_segments"][0].item())
         seg = r["seg"][0]
-        feat = r["feat"][0, :n]
+        if self._segmentation_type in ("none", None):
+            n, feat = seg.numel(), None
+        else:
+            n = int(r["n_segments"][0].item())
+            feat = r["feat"][0, :n]
         dense = r["dense"] if kwargs.get("return_dense_features", False) else None
         if self._segmentation_type == "random":
             return None, feat, seg, None, dense
+        if self._segmentation_type in ("none", None):   # segment_pixelwise: dense features are the features (:389-396)
+            return r["edges"].T, r["feat"], seg, r["centers"], dense
         ne = int(r["n_edges"][0].item())
         if ne < 0:  # the kernel flags an edge-buffer overflow with -(true count) instead of dropping edges silently
             raise RuntimeError(f"adjacency list has {-ne} edges, more than the buffer of {r['edges'].shape[1]}")
@@ -139,9 +149,32 @@ class FeatureExtractor:
             seg = seg.reshape(B, H, W)
             smax = nr
             counts = torch.full((B,), nr, device=img.device, dtype=torch.int32)
-        else:  # pixel-wise ("none"): every pixel is its own segment — dense features are the features
-            raise ValueError("segmentation_type 'none' returns dense features; call DinoInterface.inference "
-                             "or TraversabilityInference (per-pixel path) instead")
+        elif self._segmentation_type == "slic":
+            if img.dtype == torch.uint8:
+                raise ValueError("slic segmentation takes the resized float image (B,3,H,W), as the reference passes it")
+            K = self._slic_num_components
+            seg = ops.slic(img, K, self._slic_compactness, self._slic_iters)
+            _, nx, ny = ops.slic_geometry(H, W, K)
+            smax = nx * ny
+            counts = ops.relabel(seg, smax)   # clusters that lost all their pixels leave no gap (no NaN feature rows)
+        else:  # pixel-wise ("none" / None, segment_pixelwise :179-196): every pixel is its own segment
+            assert B == 1, "pixel-wise segmentation is single-frame (200 704 nodes per 448x448 frame)"
+            dev = img.device
+            seg = torch.arange(0, H * W, device=dev).reshape(1, H, W)
+            ys, xs = torch.arange(H, device=dev, dtype=torch.int32), torch.arange(W, device=dev, dtype=torch.int32)
+            centers = torch.stack((ys[:, None].expand(H, W).reshape(-1), xs[None, :].expand(H, W).reshape(-1)), 1)  # (y, x)
+            s0 = seg[0]
+            hor = torch.stack((s0[:, :-1].reshape(-1), s0[:, 1:].reshape(-1)), 1)
+            ver = torch.stack((s0[:-1, :].reshape(-1), s0[1:, :].reshape(-1)), 1)
+            edges = torch.cat((hor, ver), 0)
+            if self._feature_type == "stego":
+                self._stego._forward(img, want_linear=False)
+                tokens = self._stego.code_tokens
+            else:
+                tokens = self._dino.inference_tokens(img)
+            dense = ops.upsample_dense(tokens, g, g, H, H)
+            return {"seg": seg, "feat": dense, "centers": centers, "edges": edges, "n_edges": None, "n_segments": None,
+                    "tokens": tokens, "dense": dense}
         # 2. features
         if tokens is None:
             if self._feature_type == "stego":

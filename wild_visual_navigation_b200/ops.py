@@ -128,6 +128,47 @@ def pool_supervision(seg: torch.Tensor, mask: torch.Tensor, smax: int):
     return y, valid.bool()
 
 
+_slic_luts = {}
+
+
+def slic_tables():
+    """Host lookup tables of the library's 8-bit sRGB -> CIELAB conversion as int32 numpy arrays (g256, m9, f4096)."""
+    import ctypes
+
+    import numpy as np
+
+    g, m, f = np.zeros(256, np.int32), np.zeros(9, np.int32), np.zeros(4096, np.int32)
+    lib().wvn_slic_tables(g.ctypes.data_as(ctypes.c_void_p), m.ctypes.data_as(ctypes.c_void_p),
+                          f.ctypes.data_as(ctypes.c_void_p))
+    return g, m, f
+
+
+def slic_geometry(h, w, num_components):
+    """-> (grid interval S, nx, ny); the segmentation has nx * ny clusters."""
+    import ctypes
+
+    S, nx, ny = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(lib().wvn_slic_geometry(h, w, num_components, ctypes.byref(S), ctypes.byref(nx), ctypes.byref(ny)))
+    return S.value, nx.value, ny.value
+
+
+def slic(img, num_components=100, compactness=10.0, iters=10):
+    """SLIC superpixels of img (B,3,H,W) fp32 in [0,1] -> labels (B,H,W) int64 in [0, nx*ny) (see include/wvn_b200.h)."""
+    _C.require_device()
+    B, C, H, W = img.shape
+    assert C == 3 and img.dtype == torch.float32
+    img = img.contiguous()
+    key = str(img.device)
+    if key not in _slic_luts:
+        _slic_luts[key] = tuple(torch.from_numpy(t).to(img.device) for t in slic_tables())
+    g, m, f = _slic_luts[key]
+    ws = _workspace("slic", lib().wvn_slic_workspace_bytes(B, H, W, num_components), img.device)
+    labels = torch.empty(B, H, W, device=img.device, dtype=torch.int64)
+    check(lib().wvn_slic(ptr(img), B, H, W, num_components, float(compactness), iters, ptr(g), ptr(m), ptr(f), ptr(labels),
+                         ptr(ws), stream()))
+    return labels
+
+
 def project_and_render(sK, pose_camera_in_world, points, colors, h, w, render=True, supervision=None, traversability=None):
     """Footprint projection + rasterisation (ImageProjector.project_and_render, image_projector.py:152-197).
     sK (B,4,4) scaled camera matrices, pose (B,4,4), points (B,N,3), colors (B,3) | (3,) | None.
