@@ -421,7 +421,7 @@ def run_b200(args):
                 "d2h": "trav + conf maps, int32 segment image, pooled features, centers, edges (+ counts), loss metrics"},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
         "clocks": clocks,
-        "roofline": {"kernel": {"1": "attention_kernel", "2": "attention2_kernel", "3": "attention3_kernel"}.get(os.environ.get("WVN_ATTN_IMPL", "3"), "?") + " (fused QK^T-softmax-PV, tcgen05)", "bound": "tensor",
+        "roofline": {"kernel": {"1": "attention_kernel", "2": "attention2_kernel", "3": "attention3_kernel", "5": "attention5_kernel"}.get(os.environ.get("WVN_ATTN_IMPL", "5"), "?") + " (fused QK^T-softmax-PV, tcgen05)", "bound": "tensor",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                      "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside the step)",
                      "traffic": traffic, "avg_launch_ms": attn_avg_ms, "launches": int(prof_n[0]),

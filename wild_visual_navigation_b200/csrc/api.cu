@@ -149,17 +149,19 @@ int wvn_gemm_bf16(const void* a, long long lda, const void* w, const float* bias
 #endif
 #ifdef WVN_GEMM_TIMING
   static long long* tbuf = nullptr;  // device memory: the probes must not fault on managed pages
-  if (!tbuf) cudaMalloc(&tbuf, 8 * sizeof(long long));
-  cudaMemsetAsync(tbuf, 0, 8 * sizeof(long long), S(stream));
+  if (!tbuf) cudaMalloc(&tbuf, 16 * sizeof(long long));
+  cudaMemsetAsync(tbuf, 0, 16 * sizeof(long long), S(stream));
   g.timing = tbuf;
   const int rc = gemm_bf16(g, a, lda, w, block_n, S(stream));
-  long long t[8];
+  long long t[16];
   cudaMemcpyAsync(t, tbuf, sizeof(t), cudaMemcpyDeviceToHost, S(stream));
   cudaStreamSynchronize(S(stream));
   const long long nt = t[3] > 0 ? t[3] : 1;
   fprintf(stderr, "[gemm timing M=%d N=%d K=%d kind=%d act=%d, cycles per tile of CTA 0 (%lld tiles)] mma: wait_acc_empty %lld  "
-          "wait_full(TMA) %lld  issue+commit %lld | epilogue: wait_acc_full %lld  work %lld\n",
-          m, n, k, out_kind, act, nt, t[0] / nt, t[1] / nt, t[2] / nt, t[4] / nt, t[5] / nt);
+          "wait_full(TMA) %lld  issue+commit %lld | epilogue: wait_acc_full %lld  work %lld = ldtm %lld  bias %lld  act %lld  "
+          "transpose+store %lld\n",
+          m, n, k, out_kind, act, nt, t[0] / nt, t[1] / nt, t[2] / nt, t[4] / nt, t[5] / nt, t[8] / nt, t[9] / nt, t[10] / nt,
+          t[11] / nt);
   return rc;
 #else
   return gemm_bf16(g, a, lda, w, block_n, S(stream));
@@ -190,15 +192,11 @@ int wvn_attention_bf16(const void* q, const void* k, const void* vt, void* out, 
               "mma: issue_qk(+waits) %lld  wait_p %lld  wait_v+issue_pv %lld  loop %lld\n",
               timing_buf[0] / nkv, timing_buf[1] / nkv, timing_buf[2] / nkv, timing_buf[3] / nkv, timing_buf[4] / nkv,
               timing_buf[8] / nkv, timing_buf[9] / nkv, timing_buf[10] / nkv, timing_buf[11] / nkv);
-    else if (impl && atoi(impl) == 6)
-      fprintf(stderr, "[attn v6 timing, cycles per 32-key step, thread 0] wait_s %lld  ldtm %lld  max+rescale %lld  exp %lld  wait_pv+store %lld\n",
-              timing_buf[0] / ((n_valid + 31) / 32), timing_buf[1] / ((n_valid + 31) / 32), timing_buf[2] / ((n_valid + 31) / 32),
-              timing_buf[3] / ((n_valid + 31) / 32), timing_buf[4] / ((n_valid + 31) / 32));
-    else if (impl && atoi(impl) == 5)
+    else if (impl == nullptr || atoi(impl) == 5)
       fprintf(stderr, "[attn v5 timing, cycles per 64-key tile, thread 0] wait_s %lld  ldtm %lld  max+rescale %lld  exp %lld  store %lld\n",
               timing_buf[0] / ((n_valid + 63) / 64), timing_buf[1] / ((n_valid + 63) / 64), timing_buf[2] / ((n_valid + 63) / 64),
               timing_buf[3] / ((n_valid + 63) / 64), timing_buf[4] / ((n_valid + 63) / 64));
-    else if (impl == nullptr || atoi(impl) == 3)
+    else if (atoi(impl) == 3)
       fprintf(stderr, "[attn v3 timing, cycles per KV tile, thread 0] wait_s %lld  ldtm %lld  max+mailbox %lld  rescale %lld  exp %lld  "
               "probe+wait_pv+store %lld\n", timing_buf[0] / nkv, timing_buf[1] / nkv, timing_buf[2] / nkv, timing_buf[5] / nkv,
               timing_buf[3] / nkv, timing_buf[4] / nkv);

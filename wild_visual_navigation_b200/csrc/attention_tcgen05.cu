@@ -1557,311 +1557,6 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   }
 }
 
-
-// =====================================================================================================================
-// v6 (round 2): v5's four co-resident CTAs with 32-key compute sub-tiles and S, P in SEPARATE tensor-memory columns.
-//
-// v5's phase timers: a softmax thread waits ~900 of its ~2450 clk per 64-key tile for S(j+1), because Q·K^T(j+1) can
-// only be queued behind P·V(j) when P overwrites S.  With 32 keys per step, S (32 columns) + P (16) + O (64) fit the 128
-// columns of a CTA side by side, so Q·K^T(j+1) is issued as soon as the scores of step j are in registers (v1's early
-// issue) and runs under the exponentials.  TMA still moves 64-key K / V^T tiles; the two halves of a tile are addressed
-// through the UMMA descriptors (K rows +32 = +4 KB; V^T k-slices 2, 3).
-// =====================================================================================================================
-namespace v6 {
-constexpr int kSub = 32;                          // keys per compute step
-constexpr uint32_t kColS = 0, kColP = 32, kColO = 64;
-}  // namespace v6
-
-struct SoftmaxCtx6 {
-  uint32_t tmem_s, tmem_p, tmem_o;
-  float sl2;
-  uint64_t *s_full, *s_free, *p_full, *pv_done;
-  float m_ref, l;
-};
-
-template <int POLY, bool MASKED>
-__device__ __forceinline__ void softmax_tile6(SoftmaxCtx6& c, int t, int valid, long long* tph, bool timing, long long& tprev) {
-#ifdef WVN_ATTN_TIMING
-#define WVN_TPH(i) if (timing) { const long long tn = clock64(); tph[i] += tn - tprev; tprev = tn; }
-#else
-#define WVN_TPH(i)
-#endif
-  mbar_wait(c.s_full, t & 1);
-  tc_fence_after();
-  WVN_TPH(0)
-  uint32_t sr[32];
-  tmem_ld32(c.tmem_s, sr);
-  tmem_ld_wait();
-  tc_fence_before();
-  mbar_arrive(c.s_free);   // the scores are in registers: Q·K^T(t+1) may overwrite S while the exponentials run
-  WVN_TPH(1)
-
-  float mx;
-  if (!MASKED) {
-    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      m0 = max3(m0, __uint_as_float(sr[i]), __uint_as_float(sr[i + 1]));
-      m1 = max3(m1, __uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3]));
-      m2 = max3(m2, __uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5]));
-      m3 = max3(m3, __uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7]));
-    }
-    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-  } else {
-    mx = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (i < valid) ? __uint_as_float(sr[i]) : -INFINITY);
-  }
-  bool waited_pv = false;
-  if (t == 0) {
-    c.m_ref = mx;
-  } else {
-    const float m_new = fmaxf(c.m_ref, mx);
-    const bool need = (m_new - c.m_ref) * c.sl2 > kRescaleThreshold;
-    if (__any_sync(0xffffffffu, need)) {
-      mbar_wait(c.pv_done, (t - 1) & 1);   // O must be quiescent
-      waited_pv = true;
-      tc_fence_after();
-      const float alpha = need ? fast_exp2((c.m_ref - m_new) * c.sl2) : 1.f;
-      if (need) c.m_ref = m_new;
-      c.l *= alpha;
-#pragma unroll 1
-      for (int q = 0; q < 2; ++q) {
-        uint32_t r[32];
-        tmem_ld32(c.tmem_o + q * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-        tmem_st32(c.tmem_o + q * 32, r);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-    }
-  }
-  WVN_TPH(2)
-
-  const float mb2 = c.m_ref * c.sl2;
-  uint32_t pr[16];
-  if (!MASKED) {
-    const uint64_t sl2_2 = pack2(c.sl2, c.sl2), nmb2 = pack2(-mb2, -mb2);
-    uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const uint64_t x2 = fma2(pack2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), sl2_2, nmb2);
-      float e0, e1;
-      if (POLY == 9) {
-        unpack2(x2, e0, e1);
-      } else if (((i >> 1) & 7) < POLY) {
-        poly_exp2_pair(x2, e0, e1);
-      } else {
-        float x0, x1;
-        unpack2(x2, x0, x1);
-        e0 = fast_exp2(x0);
-        e1 = fast_exp2(x1);
-      }
-      if ((i >> 1) & 1) lb = add2(lb, pack2(e0, e1)); else la = add2(la, pack2(e0, e1));
-      pr[i >> 1] = pack_bf16x2(e0, e1);
-    }
-    float s0, s1;
-    unpack2(add2(la, lb), s0, s1);
-    c.l += s0 + s1;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const float e0 = (i < valid) ? fast_exp2(fmaf(__uint_as_float(sr[i]), c.sl2, -mb2)) : 0.f;
-      const float e1 = (i + 1 < valid) ? fast_exp2(fmaf(__uint_as_float(sr[i + 1]), c.sl2, -mb2)) : 0.f;
-      c.l += e0 + e1;
-      pr[i >> 1] = pack_bf16x2(e0, e1);
-    }
-  }
-  WVN_TPH(3)
-  if (t > 0 && !waited_pv) mbar_wait(c.pv_done, (t - 1) & 1);   // P·V(t-1) has read the P columns
-  tmem_st16(c.tmem_p, pr);
-  tmem_st_wait();
-  tc_fence_before();
-  mbar_arrive(c.p_full);
-  WVN_TPH(4)
-#undef WVN_TPH
-}
-
-template <int POLY>
-__global__ void __launch_bounds__(v5::kThreads, 4)
-attention6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                  const __grid_constant__ CUtensorMap tmap_vt, const AttnArgs args) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + v5::kOffBar);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = k_full + v5::kStages;
-  uint64_t* v_full = k_empty + v5::kStages;
-  uint64_t* v_empty = v_full + v5::kStages;
-  uint64_t* s_full = v_empty + v5::kStages;
-  uint64_t* s_free = s_full + 1;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* pv_done = s_full + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q_tile = args.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
-  const int bh = args.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
-  const int nsub = (args.n_valid + v6::kSub - 1) / v6::kSub;   // compute steps; steps of pure padding are never touched
-  const int nkv = (nsub + 1) / 2;                               // 64-key tiles to load
-
-  if (warp == v5::kWarpMma && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < v5::kStages; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == v5::kWarpTma) tmem_alloc(tmem_slot, v5::kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == v5::kWarpTma) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(v5::kRegsAux));
-    const int row0 = bh * args.npad;
-    if (elect_one_sync()) {
-      tma_prefetch_desc(&tmap_q);
-      tma_prefetch_desc(&tmap_k);
-      tma_prefetch_desc(&tmap_vt);
-      mbar_arrive_expect_tx(q_full, kQBytes);
-      tma_load_2d(&tmap_q, q_full, smem + kOffQ, 0, row0 + q_tile * kTileQ);
-    }
-    __syncwarp();
-    for (int j = 0; j < nkv; ++j) {
-      const int st = j % v5::kStages;
-      const uint32_t ph = (j / v5::kStages) & 1;
-      mbar_wait(&k_empty[st], ph ^ 1);
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&k_full[st], v5::kKBytes);
-        tma_load_2d(&tmap_k, &k_full[st], smem + v5::kOffK + st * v5::kKBytes, 0, row0 + j * v5::kTileKV);
-      }
-      __syncwarp();
-      mbar_wait(&v_empty[st], ph ^ 1);
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&v_full[st], v5::kVBytes);
-        tma_load_2d(&tmap_vt, &v_full[st], smem + v5::kOffV + st * v5::kVBytes, j * v5::kTileKV, bh * kDh);
-      }
-      __syncwarp();
-    }
-  } else if (warp == v5::kWarpMma) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(v5::kRegsAux));
-    constexpr uint32_t idesc_s = make_idesc_bf16(kTileQ, v6::kSub);   // 128 x 32 keys
-    constexpr uint32_t idesc_o = make_idesc_bf16(kTileQ, kDh);        // 128 x 64 channels
-    const uint32_t tmem_s = tmem_base + v6::kColS;
-    const uint32_t tmem_p = tmem_base + v6::kColP;
-    const uint32_t tmem_o = tmem_base + v6::kColO;
-    const uint64_t desc_q = make_sw128_kmajor_desc(smem_u32(smem + kOffQ));
-    auto issue_qk = [&](int t) {
-      const int j = t >> 1, h = t & 1;
-      const int st = j % v5::kStages;
-      const uint32_t ph = (j / v5::kStages) & 1;
-      if (h == 0) mbar_wait(&k_full[st], ph);
-      if (t > 0) mbar_wait(s_free, (t - 1) & 1);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        // rows [32 h, 32 h + 32) of the 64-key K tile: 32 rows x 128 B = 4 KB further (whole 1 KB swizzle atoms)
-        const uint64_t desc_k = make_sw128_kmajor_desc(smem_u32(smem + v5::kOffK + st * v5::kKBytes + h * 4096));
-#pragma unroll
-        for (int k = 0; k < kDh / 16; ++k) umma_bf16_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc_s, k != 0);
-        if (h == 1 || t == nsub - 1) umma_commit(&k_empty[st]);
-        umma_commit(s_full);
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    issue_qk(0);
-    for (int t = 0; t < nsub; ++t) {
-      if (t + 1 < nsub) issue_qk(t + 1);
-      const int j = t >> 1, h = t & 1;
-      const int st = j % v5::kStages;
-      const uint32_t ph = (j / v5::kStages) & 1;
-      mbar_wait(p_full, t & 1);
-      if (h == 0) mbar_wait(&v_full[st], ph);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint64_t desc_v = make_sw128_kmajor_desc(smem_u32(smem + v5::kOffV + st * v5::kVBytes));
-#pragma unroll
-        for (int k = 0; k < 2; ++k)   // k-slices 2 h, 2 h + 1 of the 64-key V^T tile
-          umma_bf16_ts(tmem_o, tmem_p + 8 * k, desc_v + 2 * (2 * h + k), idesc_o, (t | k) != 0);
-        if (h == 1 || t == nsub - 1) umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
-      }
-      __syncwarp();
-    }
-  } else if (warp >= 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(v5::kRegsAux));
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(v5::kRegsSoftmax));
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    SoftmaxCtx6 c;
-    c.tmem_s = tmem_base + lane_base + v6::kColS;
-    c.tmem_p = tmem_base + lane_base + v6::kColP;
-    c.tmem_o = tmem_base + lane_base + v6::kColO;
-    c.sl2 = args.scale_log2;
-    c.s_full = s_full; c.s_free = s_free; c.p_full = p_full; c.pv_done = pv_done;
-    c.m_ref = -INFINITY;
-    c.l = 0.f;
-#ifdef WVN_ATTN_TIMING
-    const bool timing = args.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
-    long long tph[6] = {0, 0, 0, 0, 0, 0}, tprev = timing ? clock64() : 0;
-#else
-    constexpr bool timing = false;
-    long long* tph = nullptr;
-    long long tprev = 0;
-#endif
-    const int tail = args.n_valid - (nsub - 1) * v6::kSub;   // valid keys of the last step, 1..32
-#pragma unroll 1
-    for (int t = 0; t < nsub - 1; ++t) softmax_tile6<POLY, false>(c, t, v6::kSub, tph, timing, tprev);
-    if (tail == v6::kSub) softmax_tile6<POLY, false>(c, nsub - 1, tail, tph, timing, tprev);
-    else softmax_tile6<(POLY == 9 ? 9 : 0), true>(c, nsub - 1, tail, tph, timing, tprev);
-#ifdef WVN_ATTN_TIMING
-    if (timing)
-      for (int i = 0; i < 6; ++i) args.timing[i] = tph[i];
-#endif
-    const float inv_l = 1.f / c.l;
-    mbar_wait(pv_done, (nsub - 1) & 1);
-    tc_fence_after();
-    const int b = bh / args.heads;
-    const int h = bh - b * args.heads;
-    const long long q_idx = static_cast<long long>(b) * args.npad + q_tile * kTileQ + warp * 32 + lane;
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + q_idx * args.ldo + h * kDh;
-#pragma unroll 1
-    for (int q = 0; q < 2; ++q) {
-      uint32_t r[32];
-      tmem_ld32(c.tmem_o + q * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i4 = 0; i4 < 4; ++i4) {
-        float f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[8 * i4 + i]) * inv_l;
-        st_global_v4(dst + q * 32 + 8 * i4, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                     pack_bf16x2(f[6], f[7]));
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == v5::kWarpTma) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, v5::kTmemCols);
-  }
-}
-
-
 }  // namespace
 
 int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* vt, cudaStream_t stream) {
@@ -1881,14 +1576,15 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
     poly = e ? atoi(e) : kDefaultPoly;
     if ((poly < 0 || poly > 4) && poly != 9) poly = kDefaultPoly;
   }
-  // $WVN_ATTN_IMPL: 3 (default) = one query tile per CTA, 2 CTAs per SM, two threads per query row;
-  // 1 = the same with one thread per row (round 1's structure); 2 = one CTA per SM owning two query tiles with ordered
-  // softmax warpgroups.  All three are parity-tested; measured on B200 (B = 32, stand-alone): 766 / 750 / 720 TFLOP/s
+  // $WVN_ATTN_IMPL: 5 (default) = four co-resident CTAs per SM, 64-key tiles, P over S; 3 = one query tile per CTA, two CTAs
+  // per SM, two threads per query row; 1 = the same with one thread per row (round 1's structure); 2 = one CTA per SM owning
+  // two query tiles with ordered softmax warpgroups.  All are parity-tested; measured on B200 (B = 32, stand-alone):
+  // 873 / 766 / 750 / 720 TFLOP/s.
   static int impl = -1;
   if (impl < 0) {
     const char* e = getenv("WVN_ATTN_IMPL");
-    impl = e ? atoi(e) : 3;
-    if (impl != 1 && impl != 2 && impl != 3 && impl != 5 && impl != 6) impl = 3;
+    impl = e ? atoi(e) : 5;
+    if (impl != 1 && impl != 2 && impl != 3 && impl != 5) impl = 5;
   }
   static int no_token = -1;  // $WVN_ATTN_TOKEN=0: let the two softmax warpgroups free-run (A/B of the exp-phase ordering)
   if (no_token < 0) {
@@ -1899,7 +1595,7 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
   a2.no_token = no_token;
   const int ntiles = a.npad / kTileQ;
   dim3 grid(impl == 2 ? (ntiles + 1) / 2 : ntiles, static_cast<unsigned>(bh));
-  const bool four = impl == 5 || impl == 6;   // the four-CTAs-per-SM kernels share their geometry
+  const bool four = impl == 5;
   const int threads = impl == 2 ? v2::kThreads : (impl == 3 ? v3::kThreads : (four ? v5::kThreads : kThreads));
   const uint32_t smem_bytes =
       impl == 2 ? v2::kSmemBytes : (impl == 3 ? v3::kSmemBytes : (four ? v5::kSmemBytes : kSmemBytes));
@@ -1919,15 +1615,6 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
       case 3: WVN_PROPAGATE(launch(attention2_kernel<3>)); break;
       case 4: WVN_PROPAGATE(launch(attention2_kernel<4>)); break;
       default: WVN_PROPAGATE(launch(attention2_kernel<9>)); break;
-    }
-  } else if (impl == 6) {
-    switch (poly) {
-      case 0: WVN_PROPAGATE(launch(attention6_kernel<0>)); break;
-      case 1: WVN_PROPAGATE(launch(attention6_kernel<1>)); break;
-      case 2: WVN_PROPAGATE(launch(attention6_kernel<2>)); break;
-      case 3: WVN_PROPAGATE(launch(attention6_kernel<3>)); break;
-      case 4: WVN_PROPAGATE(launch(attention6_kernel<4>)); break;
-      default: WVN_PROPAGATE(launch(attention6_kernel<9>)); break;
     }
   } else if (impl == 5) {
     switch (poly) {

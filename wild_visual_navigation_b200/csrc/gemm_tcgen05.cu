@@ -120,15 +120,36 @@ __device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
 // One 128 x BN accumulator tile: TMEM -> registers -> bias / activation -> global memory.  Called by the kEpiWarps
 // epilogue warps (ewarp & 3 must equal the hardware warp's TMEM lane quarter); the kEpiGroups warps of a lane
 // quarter interleave the tile's 32-column chunks.  m_blk / n_blk locate the tile in C.
+template <int BN>
+struct EpiChunks {
+  static constexpr int kPerThread = (BN + 32 * kEpiGroups - 1) / (32 * kEpiGroups);
+};
+
+// The bias of a warp's 32-column chunks, one column per lane (a single coalesced 128-byte load per chunk).  Issued
+// BEFORE the wait for the accumulator: with ~220 KB of the SM's L1 carved out as shared memory the bias vector does not
+// survive in L1 between tiles, and the 8 float4 loads per lane this replaces cost ~700 clk of L2 latency per chunk on the
+// epilogue's critical path (round-2 phase timing: 1400 of 4400 clk per QKV tile).
+template <int BN>
+__device__ __forceinline__ void epilogue_prefetch_bias(const GemmArgs& args, const int n_blk, const int ewarp, const int lane,
+                                                       float (&bias_lane)[EpiChunks<BN>::kPerThread]) {
+  const int group = ewarp >> 2;
+#pragma unroll
+  for (int chunk_i = 0; chunk_i < EpiChunks<BN>::kPerThread; ++chunk_i) {
+    const int c0 = 32 * (group + kEpiGroups * chunk_i);
+    bias_lane[chunk_i] = (args.bias != nullptr && c0 < BN) ? __ldg(args.bias + n_blk * BN + c0 + lane) : 0.f;
+  }
+}
+
 template <int BN, int EPI, int ACT>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32_t tmem_acc, const int m_blk, const int n_blk,
-                                              const int ewarp, const int lane, uint8_t* epi_stage, float& head_partial) {
+                                              const int ewarp, const int lane, uint8_t* epi_stage, float& head_partial,
+                                              const float (&bias_lane)[EpiChunks<BN>::kPerThread]) {
   const int quarter = ewarp & 3;  // TMEM lane quarter this warp may access
   const int group = ewarp >> 2;   // which of the interleaved 32-col chunk sets
   const int row_in_tile = quarter * 32 + lane;
   const int row = m_blk * BM + row_in_tile;
   const bool row_ok = row < args.M;
-  constexpr int kChunksPerThread = (BN + 32 * kEpiGroups - 1) / (32 * kEpiGroups);
+  constexpr int kChunksPerThread = EpiChunks<BN>::kPerThread;
 
   // Per-row destination bookkeeping
   long long out_row = row;
@@ -145,6 +166,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
 #ifdef WVN_GEMM_ABLATE
   if (args.debug == 2) return;
 #endif
+#ifdef WVN_GEMM_TIMING
+  const bool etiming = args.timing != nullptr && blockIdx.x == 0 && ewarp == 0 && lane == 0;
+  long long eprev = clock64();
+#define WVN_ETM(i) if (etiming) { const long long tn = clock64(); args.timing[8 + i] += tn - eprev; eprev = tn; }
+#else
+#define WVN_ETM(i)
+#endif
 #pragma unroll
   for (int chunk_i = 0; chunk_i < kChunksPerThread; ++chunk_i) {
     const int c0 = 32 * (group + kEpiGroups * chunk_i);
@@ -152,19 +180,38 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
     const int col0 = n_blk * BN + c0;
     uint32_t r[32];
     tmem_ld32(tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + c0, r);
+    // While the accumulator load is in flight: the chunk's 32 bias values (one per lane, prefetched before the wait for
+    // the accumulator) go through the warp's staging tile and come back to every lane as 8 broadcast 16-byte reads.
+    constexpr bool kBiasViaSmem = epi_buf_bytes(EPI) >= 128;   // epilogues without a staging tile broadcast by shuffle
+    uint4 bq[8];
+    if (kBiasViaSmem && args.bias != nullptr) {
+      const uint32_t bbuf = smem_u32(epi_stage) + ewarp * epi_buf_bytes(EPI);
+      __syncwarp();  // the previous chunk's read-back of the staging tile is complete
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(bbuf + lane * 4), "f"(bias_lane[chunk_i]) : "memory");
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bq[j] = lds128(bbuf + 16 * j);
+    }
     tmem_ld_wait();
     tmem_ld_fence32(r);
+    WVN_ETM(0)
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (args.bias != nullptr) {
-      const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
+    if (!kBiasViaSmem && args.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane[chunk_i], j);
+    }
+    if (kBiasViaSmem && args.bias != nullptr) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(b4 + j);
-        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        float a0, a1, a2, a3;
+        unpack2(add2(pack2(v[4 * j], v[4 * j + 1]), pack2(__uint_as_float(bq[j].x), __uint_as_float(bq[j].y))), a0, a1);
+        unpack2(add2(pack2(v[4 * j + 2], v[4 * j + 3]), pack2(__uint_as_float(bq[j].z), __uint_as_float(bq[j].w))), a2, a3);
+        v[4 * j] = a0; v[4 * j + 1] = a1; v[4 * j + 2] = a2; v[4 * j + 3] = a3;
       }
     }
+    WVN_ETM(1)
     if (ACT == ACT_RELU) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -172,6 +219,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
 #pragma unroll
       for (int j = 0; j < 32; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
     }
+    WVN_ETM(2)
     // ---- coalesced stores: the 32x32 chunk (lane = row) is transposed through a swizzled shared-
     // memory tile so that each store instruction writes whole row segments (lanes along columns).
     // Per-thread row-wise stores were LSU-wavefront-bound — every 16-byte piece of a lane lies in a
@@ -238,6 +286,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
         }
       }
     }
+    WVN_ETM(3)
     if (!row_ok) {
       // out-of-range tail row: no per-row work below
     } else if (EPI == EPI_PATCH) {
@@ -423,13 +472,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #ifdef WVN_GEMM_TIMING
       long long et0 = clock64();
 #endif
+      float bias_lane[EpiChunks<BN>::kPerThread];
+      epilogue_prefetch_bias<BN>(args, it.n_blk, ewarp, lane, bias_lane);
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
 #ifdef WVN_GEMM_TIMING
       long long et1 = clock64();
 #endif
       const int m_eff = args.reverse_m ? num_m - 1 - it.m_blk : it.m_blk;
-      epilogue_tile<BN, EPI, ACT>(args, tmem_base + acc * BN, m_eff, it.n_blk, ewarp, lane, epi_stage, head_partial);
+      epilogue_tile<BN, EPI, ACT>(args, tmem_base + acc * BN, m_eff, it.n_blk, ewarp, lane, epi_stage, head_partial,
+                                  bias_lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
