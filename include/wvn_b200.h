@@ -307,6 +307,13 @@ void wvn_mlp_trainer_destroy(wvn_mlp_trainer_t* t);
  * wvn_comm_unique_id, the caller broadcasts it by any means, every rank calls wvn_mlp_trainer_init_comm. */
 int wvn_comm_unique_id(void* id128);
 int wvn_mlp_trainer_init_comm(wvn_mlp_trainer_t* t, const void* id128, int rank, int world);
+/* ConfidenceGenerator method of the fused step (utils/confidence_generator.py:49-76): 0 latest_measurement (default),
+ * 1 running_mean (:94-115), 2 kalman_filter (:131-145 with utils/kalman_filter.py:78-111, D = 1, F = H = 1; kf_proc_cov /
+ * kf_meas_cov = its Q / R), 3 moving_average (:117-129, window of 5 steps kept inside the trainer).  The state the
+ * reference keeps in module parameters is read and updated in place through these device pointers — var (1,1) fp32;
+ * running_n / running_sum / running_sum_of_squares (1,) fp64 — each may be NULL (the trainer then keeps a private copy). */
+int wvn_mlp_trainer_set_confidence(wvn_mlp_trainer_t* t, int method, float* var, double* running_n, double* running_sum,
+                                   double* running_sum_of_squares, float kf_proc_cov, float kf_meas_cov);
 int wvn_mlp_train_step(wvn_mlp_trainer_t* t, float* params, float* exp_avg, float* exp_avg_sq, long long* step_counter,
                        const float* x, int groups, int rows_per_group, const int* n_rows, const float* y,
                        const unsigned char* y_valid, float* cg_mean, float* cg_std, float* confidence_out,

@@ -181,18 +181,67 @@ def confidence_inference(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor,
     return (1 - ((xc - lo) / (hi - lo))).float()
 
 
+class ConfidenceState:
+    """``ConfidenceGenerator`` (utils/confidence_generator.py:13-212) as a plain state machine: ``update(x, x_positive)``
+    for the four methods — latest_measurement :78-82, running_mean :94-115, moving_average :117-129 (window 5),
+    kalman_filter :131-145 with ``KalmanFilter`` (utils/kalman_filter.py:78-111; D = 1, proc_model 1, proc_cov 0.2,
+    meas_model 1, meas_cov 1, no outlier rejection) — with the reference's dtypes (float32 state, float64 running sums)."""
+
+    def __init__(self, std_factor: float, method: str = "latest_measurement"):
+        assert method in ("latest_measurement", "running_mean", "moving_average", "kalman_filter")
+        self.std_factor, self.method = std_factor, method
+        self.mean, self.var, self.std = torch.zeros(1), torch.ones(1, 1), torch.ones(1)
+        self.running = torch.zeros(3, dtype=torch.float64)      # n, sum, sum of squares
+        self.window = []                                        # the deque(maxlen=5) of x_positive tensors
+        self.kf_proc_cov, self.kf_meas_cov = 0.2, 1.0
+
+    def update(self, x: torch.Tensor, xp: torch.Tensor) -> torch.Tensor:
+        x, xp = x.detach(), xp.detach()
+        m = self.method
+        if m == "latest_measurement":
+            self.mean[0], self.std[0] = xp.mean(), xp.std()
+            return confidence_inference(x, self.mean, self.std, self.std_factor)
+        if m == "running_mean":
+            self.running += torch.stack([torch.tensor(float(xp.numel()), dtype=torch.float64), xp.sum().double(),
+                                         (xp ** 2).sum().double()])
+            self.mean[0] = self.running[1] / self.running[0]
+            self.var[0] = self.running[2:3] / self.running[0] - self.mean ** 2     # float64 - float32 -> float64 -> float32
+            self.std[0] = torch.sqrt(self.var)[0, 0]
+            return confidence_inference(x, self.mean, self.std, self.std_factor)
+        if m == "moving_average":
+            self.window = (self.window + [xp])[-5:]
+            w = torch.cat(self.window, dim=0)
+            self.mean[0], self.std[0] = w.mean(), w.std()
+            xc = torch.clip(x, self.mean - 2 * self.std, self.mean + 2 * self.std)
+            return ((xc - xc.min()) / (xc.max() - xc.min())).float()
+        # kalman_filter
+        if xp.shape[0] != 0:
+            meas = xp.mean()
+            state, cov = self.mean.clone(), self.var.clone() + self.kf_proc_cov        # prediction with F = 1
+            innovation = meas - state
+            gain = cov / (cov + self.kf_meas_cov)
+            self.mean[0] = (state + (gain @ innovation))[0]
+            self.var[0, 0] = ((1.0 - gain) @ cov)[0, 0]
+        self.std[0] = torch.sqrt(self.var)[0, 0]
+        conf = torch.exp(-(((x - self.mean) / (self.std * self.std_factor)) ** 2) * 0.5)
+        conf[x < self.mean] = 1.0
+        return conf.float()
+
+
 # ------------------------------------------------------------------------------------------
 # TraversabilityLoss.forward                     (utils/loss.py:93-160), anomaly_balanced, MSE
 # ------------------------------------------------------------------------------------------
-def traversability_loss(res, x, y, y_valid, w_trav=0.03, w_reco=0.5, std_factor=0.5, anomaly_balanced=True):
+def traversability_loss(res, x, y, y_valid, w_trav=0.03, w_reco=0.5, std_factor=0.5, anomaly_balanced=True, cg=None):
     """Returns (loss, aux) with aux holding loss_reco, loss_trav, loss_trav_confidence, confidence,
-    and the updated generator (mean, std) of method 'latest_measurement'."""
+    and the updated generator (mean, std).  ``cg``: a ConfidenceState carried across steps (default: a fresh
+    'latest_measurement' generator, which has no memory)."""
     D = x.shape[1]
     loss_reco = F.mse_loss(res[:, -D:], x, reduction="none").mean(dim=1)
     with torch.no_grad():
-        pos = loss_reco[y_valid]
-        mean, std = pos.mean().reshape(1), pos.std().reshape(1)
-        conf = confidence_inference(loss_reco, mean, std, std_factor)
+        if cg is None:
+            cg = ConfidenceState(std_factor)
+        conf = cg.update(loss_reco, loss_reco[y_valid])
+        mean, std = cg.mean.clone(), cg.std.clone()
     raw = F.mse_loss(res[:, :-D].squeeze(), y, reduction="none")
     labeled = raw[y_valid]
     unlabeled_w = raw[~y_valid] * (1 - conf)[~y_valid]

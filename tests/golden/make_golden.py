@@ -293,6 +293,31 @@ def make_confidence(ns):
     )
 
 
+def make_confidence_methods(ns):
+    """The reference's OWN ConfidenceGenerator for all four methods (confidence_generator.py:78-145): five consecutive
+    ``update`` calls with growing / shrinking positive sets, including an empty one for the Kalman filter."""
+    g = torch.Generator().manual_seed(23)
+    seq = []
+    for i, (n, npos) in enumerate(((300, 50), (280, 31), (310, 2), (290, 77), (305, 40), (300, 64), (150, 9))):
+        x = torch.rand(n, generator=g) * (1.5 + 0.3 * i) + 0.05 * i
+        pos = torch.rand(n, generator=g) < npos / n
+        pos[:2] = True
+        seq.append((x, pos))
+    out = {"seq": seq, "std_factor": 0.5}
+    for method in ("latest_measurement", "running_mean", "moving_average", "kalman_filter"):
+        cg = ns.ConfidenceGenerator(std_factor=0.5, method=method)
+        steps = []
+        with torch.no_grad():
+            for i, (x, pos) in enumerate(seq):
+                xp = x[pos] if not (method == "kalman_filter" and i == 2) else x[:0]   # empty positives: KF keeps its state
+                conf = cg.update(x, xp, step=i)
+                steps.append({"conf": conf.clone(), "mean": cg.mean.detach().clone(), "std": cg.std.detach().clone(),
+                              "var": cg.var.detach().clone()})
+        out[method] = steps
+        out[method + "_keys"] = sorted(cg.state_dict().keys())
+    torch.save(out, os.path.join(HERE, "confidence_methods.pt"))
+
+
 def synthetic_segments(h=48, w=48, n=9, seed=5):
     g = torch.Generator().manual_seed(seed)
     cy = torch.rand(n, generator=g) * h
@@ -472,6 +497,7 @@ if __name__ == "__main__":
     make_mlp_train(ns)
     make_mlp_init(ns)
     make_confidence(ns)
+    make_confidence_methods(ns)
     make_handoff(ns)
     make_checkpoint(ns)
     make_supervision()

@@ -1004,6 +1004,13 @@ int wvn_mlp_trainer_init_comm(wvn_mlp_trainer_t* t, const void* id128, int rank,
   return fused_trainer_init_comm(t->impl, id128, rank, world);
 }
 
+int wvn_mlp_trainer_set_confidence(wvn_mlp_trainer_t* t, int method, float* var, double* running_n, double* running_sum,
+                                   double* running_sum_of_squares, float kf_proc_cov, float kf_meas_cov) {
+  WVN_REQUIRE(t, "wvn_mlp_trainer_set_confidence: null trainer");
+  return fused_trainer_set_confidence(t->impl, method, var, running_n, running_sum, running_sum_of_squares, kf_proc_cov,
+                                      kf_meas_cov);
+}
+
 int wvn_mlp_train_step(wvn_mlp_trainer_t* t, float* params, float* exp_avg, float* exp_avg_sq, long long* step_counter,
                        const float* x, int groups, int rows_per_group, const int* n_rows, const float* y,
                        const unsigned char* y_valid, float* cg_mean, float* cg_std, float* confidence_out,

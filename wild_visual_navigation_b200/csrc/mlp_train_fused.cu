@@ -218,7 +218,17 @@ train_fwd_rows_kernel(MlpShape s, MlpOffsets o, const float* __restrict__ params
       nv += __shfl_xor_sync(0xffffffffu, nv, off);
       nr += __shfl_xor_sync(0xffffffffu, nr, off);
     }
+    // extrema of loss_reco over the live rows (non-negative doubles order like their bit patterns)
+    double lmin = ci >= 0 ? static_cast<double>(red[t] / static_cast<float>(dim)) : __longlong_as_double(0x7ff0000000000000ll);
+    double lmax = ci >= 0 ? static_cast<double>(red[t] / static_cast<float>(dim)) : 0.0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, off));
+      lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
+    }
     if (t == 0 && nr > 0.0) {
+      atomicMin(reinterpret_cast<unsigned long long*>(&sc->x_min), static_cast<unsigned long long>(__double_as_longlong(lmin)));
+      atomicMax(reinterpret_cast<unsigned long long*>(&sc->x_max), static_cast<unsigned long long>(__double_as_longlong(lmax)));
       atomicAdd(&sc->sum_lr, s1);
       atomicAdd(&sc->sum_lr2, s2);
       atomicAdd(&sc->sum_raw, sraw);
@@ -228,48 +238,107 @@ train_fwd_rows_kernel(MlpShape s, MlpOffsets o, const float* __restrict__ params
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K1b
+// ConfidenceGenerator.update from the (all-reduced) sums of this step: one thread.  utils/confidence_generator.py:
+// latest_measurement :78-82, running_mean :94-115, moving_average :117-129, kalman_filter :131-145 (+ KalmanFilter,
+// utils/kalman_filter.py:78-111 with D = 1, F = H = 1).
+__global__ void train_conf_kernel(LossCfg cfg, ConfState cs, int dim, FusedScalars* __restrict__ sc,
+                                  float* __restrict__ cg_mean, float* __restrict__ cg_std,
+                                  long long* __restrict__ step_counter) {
+  if (threadIdx.x != 0) return;
+  const double n = sc->n_valid, s1 = sc->sum_lr, s2 = sc->sum_lr2;
+  float m, sd;
+  float lo, hi, cmin = 0.f, cmax = 0.f;
+  if (cs.method == CONF_RUNNING_MEAN) {
+    const double rn = *cs.running_n + n, rs = *cs.running_sum + s1, rq = *cs.running_sumsq + s2;
+    *cs.running_n = rn; *cs.running_sum = rs; *cs.running_sumsq = rq;
+    m = static_cast<float>(rs / rn);
+    const float var = static_cast<float>(rq / rn - static_cast<double>(m * m));   // float64 - float32^2, stored as fp32
+    sd = sqrtf(var);
+    if (cs.var) *cs.var = var;
+  } else if (cs.method == CONF_KALMAN) {
+    float state = cg_mean ? *cg_mean : 0.f, cov = cs.var ? *cs.var : 1.f;
+    if (n > 0.0) {
+      const float meas = static_cast<float>(s1 / n);
+      cov = cov + cs.kf_proc_cov;                      // prediction: F = 1
+      const float gain = cov / (cov + cs.kf_meas_cov);
+      state = state + gain * (meas - state);
+      cov = (1.f - gain) * cov;
+      if (cs.var) *cs.var = cov;
+    }
+    m = state;
+    sd = sqrtf(cov);
+  } else if (cs.method == CONF_MOVING_AVERAGE) {
+    // the deque of the last kConfWindow positive sets, kept as (n, sum, sum of squares) per step
+    double* ring = cs.ring;
+    const int count = static_cast<int>(ring[3 * kConfWindow]);
+    const int slot = count % kConfWindow;
+    ring[3 * slot] = n; ring[3 * slot + 1] = s1; ring[3 * slot + 2] = s2;
+    ring[3 * kConfWindow] = count + 1;
+    double N = 0.0, S1 = 0.0, S2 = 0.0;
+    for (int i = 0; i < (count + 1 < kConfWindow ? count + 1 : kConfWindow); ++i) { N += ring[3 * i]; S1 += ring[3 * i + 1]; S2 += ring[3 * i + 2]; }
+    const double mean = S1 / N;
+    m = static_cast<float>(mean);
+    sd = N > 1.0 ? static_cast<float>(sqrt(fmax((S2 - N * mean * mean) / (N - 1.0), 0.0))) : nanf("");
+  } else {
+    const double mean = s1 / n;                                   // n == 0 -> NaN, like torch's mean of empty
+    const double var = (s2 - n * mean * mean) / (n - 1.0);        // n == 1 -> NaN, like torch.std
+    m = static_cast<float>(mean);
+    sd = (n > 1.0) ? static_cast<float>(sqrt(fmax(var, 0.0))) : nanf("");
+  }
+  if (cs.method == CONF_KALMAN) {
+    lo = m;
+    hi = 1.f / (sd * cfg.std_factor);
+  } else if (cs.method == CONF_MOVING_AVERAGE) {
+    lo = m - 2.f * sd;
+    hi = m + 2.f * sd;
+    cmin = fminf(fmaxf(static_cast<float>(sc->x_min), lo), hi);   // min / max of the clipped losses = clipped extrema
+    cmax = fminf(fmaxf(static_cast<float>(sc->x_max), lo), hi);
+  } else {
+    const float shifted = m + sd * cfg.std_factor;
+    lo = fmaxf(shifted - sd, 0.f);
+    hi = shifted + sd;
+  }
+  sc->lo = lo; sc->hi = hi; sc->cmin = cmin; sc->cmax = cmax;
+  sc->g_reco = cfg.w_reco * 2.f / (static_cast<float>(n) * static_cast<float>(dim));
+  sc->g_trav = cfg.w_trav * 2.f / static_cast<float>(sc->n_rows);
+  sc->mean = m;
+  sc->std = sd;
+  if (cg_mean) *cg_mean = m;
+  if (cg_std) *cg_std = sd;
+  *step_counter += 1;  // torch.optim.Adam counts from 1; K4 reads the bumped value
+}
+
+__device__ __forceinline__ float row_confidence(int method, float lr, float lo, float hi, float cmin, float cmax) {
+  if (method == CONF_KALMAN) {   // lo = mean, hi = 1 / (std * std_factor)
+    const float z = (lr - lo) * hi;
+    return lr < lo ? 1.f : expf(-(z * z) * 0.5f);
+  }
+  const float xc = fminf(fmaxf(lr, lo), hi);
+  if (method == CONF_MOVING_AVERAGE) return (xc - cmin) / (cmax - cmin);
+  return 1.f - (xc - lo) / (hi - lo);
+}
+
 // ------------------------------------------------------------------------------------------------ K2
-// smem (floats): dot[n3][TRP] | dh2t[h2][TR] | rowinfo[TR] | cst[8]
+// smem (floats): dot[n3][TRP] | dh2t[h2][TR] | rowinfo[TR]
 __global__ void __launch_bounds__(kThreads)
-train_bwd_rows_kernel(MlpShape s, MlpOffsets o, LossCfg cfg, const float* __restrict__ params,
+train_bwd_rows_kernel(MlpShape s, MlpOffsets o, LossCfg cfg, int conf_method, const float* __restrict__ params,
                       const float* __restrict__ x, const float* __restrict__ y,
                       const unsigned char* __restrict__ y_valid, const int* __restrict__ n_rows, int groups, int rpg,
                       const float* __restrict__ h1g, const float* __restrict__ h2g, const float* __restrict__ outg,
                       const float* __restrict__ loss_reco, const float* __restrict__ raw, float* __restrict__ d_out,
                       float* __restrict__ d_h2, float* __restrict__ d_h1, float* __restrict__ conf_out,
-                      FusedScalars* __restrict__ sc, float* __restrict__ cg_mean, float* __restrict__ cg_std,
-                      float* __restrict__ trav_w_sum, long long* __restrict__ step_counter) {
+                      const FusedScalars* __restrict__ sc, float* __restrict__ trav_w_sum) {
   extern __shared__ __align__(16) float sm[];
   const int dim = s.dim, h1 = s.h1, h2 = s.h2, n3 = s.dim + 1;
   float* dot = sm;                                 // [n3][TRP]
   float* dh2t = dot + ((n3 * TRP + 3) & ~3);       // [h2][TR], 16-byte aligned for the float4 broadcasts
   int* rinfo = reinterpret_cast<int*>(dh2t + h2 * TR);
-  float* cst = reinterpret_cast<float*>(rinfo + TR);  // lo, hi, g_reco, g_trav
   const int t = threadIdx.x;
   const int r0 = blockIdx.x * TR;
   if (t < TR) rinfo[t] = compact_index(n_rows, groups, rpg, r0 + t);
-  if (t == 0) {
-    // ConfidenceGenerator.update_latest_measurement (confidence_generator.py:78-82) from the (all-reduced) sums
-    const double n = sc->n_valid;
-    const double mean = sc->sum_lr / n;                                  // n == 0 -> NaN, like torch's mean of empty
-    const double var = (sc->sum_lr2 - n * mean * mean) / (n - 1.0);     // n == 1 -> NaN, like torch.std
-    const float m = static_cast<float>(mean);
-    const float sd = (n > 1.0) ? static_cast<float>(sqrt(fmax(var, 0.0))) : nanf("");
-    const float shifted = m + sd * cfg.std_factor;
-    cst[0] = fmaxf(shifted - sd, 0.f);
-    cst[1] = shifted + sd;
-    cst[2] = cfg.w_reco * 2.f / (static_cast<float>(n) * static_cast<float>(dim));
-    cst[3] = cfg.w_trav * 2.f / static_cast<float>(sc->n_rows);
-    if (blockIdx.x == 0) {
-      sc->mean = m;
-      sc->std = sd;
-      if (cg_mean) *cg_mean = m;
-      if (cg_std) *cg_std = sd;
-      *step_counter += 1;  // torch.optim.Adam counts from 1; K4 reads the bumped value
-    }
-  }
   __syncthreads();
-  const float lo = cst[0], hi = cst[1], g_reco = cst[2], g_trav = cst[3];
+  const float lo = sc->lo, hi = sc->hi, cmin = sc->cmin, cmax = sc->cmax, g_reco = sc->g_reco, g_trav = sc->g_trav;
   // ---- dOut (one warp per 4 rows), kept transposed in shared memory for the two products below
   {
     const int warp = t >> 5, lane = t & 31;
@@ -284,8 +353,7 @@ train_bwd_rows_kernel(MlpShape s, MlpOffsets o, LossCfg cfg, const float* __rest
       }
       const bool v = y_valid[ci] != 0;
       const float lr = loss_reco[r];
-      const float xc = fminf(fmaxf(lr, lo), hi);
-      const float conf = 1.f - (xc - lo) / (hi - lo);
+      const float conf = row_confidence(conf_method, lr, lo, hi, cmin, cmax);
       const float wgt = (v || !cfg.anomaly_balanced) ? 1.f : (1.f - conf);
       const float* orow = outg + r * n3;
       const float* xr = x + r * dim;
@@ -464,6 +532,8 @@ train_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
       metrics[0] = sc->loss_total; metrics[1] = sc->loss_trav; metrics[2] = sc->loss_reco;
       metrics[3] = sc->loss_trav_conf; metrics[4] = sc->mean; metrics[5] = sc->std;
     }
+    sc->x_min = __longlong_as_double(0x7ff0000000000000ll);   // +inf / 0: ready for the next step's atomicMin / atomicMax
+    sc->x_max = 0.0;
   }
   // torch.optim.Adam (no amsgrad, no weight decay): step t counts from 1
   const double t = static_cast<double>(*step_ptr);
@@ -493,7 +563,7 @@ struct NcclApi {
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
 };
-constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2, kNcclMin = 3;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
 NcclApi& nccl() {
   static NcclApi api;
@@ -529,6 +599,8 @@ struct FusedTrainer {
   NcclComm comm = nullptr;
   int world = 1;
   size_t smem_fwd = 0, smem_bwd = 0;
+  ConfState conf;          // ConfidenceGenerator method + where its state lives
+  double* conf_priv = nullptr;   // [3 running | 1 var as float | ring 3 * kConfWindow + 1]: private state / the ring
 };
 
 int fused_trainer_create(const MlpShape& s, int max_rows, const LossCfg& loss, const AdamCfg& adam, void* scalars_ext,
@@ -549,6 +621,21 @@ int fused_trainer_create(const MlpShape& s, int max_rows, const LossCfg& loss, c
   }
   cudaMemset(t->arena, 0, bytes);
   t->sc = scalars_ext ? reinterpret_cast<FusedScalars*>(scalars_ext) : reinterpret_cast<FusedScalars*>(t->arena);
+  {
+    FusedScalars init;
+    memset(&init, 0, sizeof(init));
+    init.x_min = INFINITY;
+    cudaMemcpy(t->sc, &init, sizeof(init), cudaMemcpyHostToDevice);
+    if (cudaMalloc(&t->conf_priv, sizeof(double) * 32) != cudaSuccess) {
+      cudaFree(t->arena);
+      delete t;
+      return set_error(WVN_ERR_CUDA, "trainer: cudaMalloc of the confidence state failed");
+    }
+    cudaMemset(t->conf_priv, 0, sizeof(double) * 32);
+    const float one = 1.f;   // private var = 1 (the reference's initial value) unless the caller binds its own
+    cudaMemcpy(reinterpret_cast<float*>(t->conf_priv + 3), &one, sizeof(float), cudaMemcpyHostToDevice);
+    fused_trainer_set_confidence(t, CONF_LATEST, nullptr, nullptr, nullptr, nullptr, 0.2f, 1.0f);
+  }
   float* f = reinterpret_cast<float*>(reinterpret_cast<char*>(t->arena) + 256);
   t->h1 = f; f += R * s.h1;
   t->d_h1 = f; f += R * s.h1;
@@ -577,7 +664,25 @@ void fused_trainer_destroy(FusedTrainer* t) {
   if (!t) return;
   if (t->comm && nccl().ok) nccl().CommDestroy(t->comm);
   if (t->arena) cudaFree(t->arena);
+  if (t->conf_priv) cudaFree(t->conf_priv);
   delete t;
+}
+
+int fused_trainer_set_confidence(FusedTrainer* t, int method, float* var, double* running_n, double* running_sum,
+                                 double* running_sumsq, float kf_proc_cov, float kf_meas_cov) {
+  WVN_REQUIRE(t, "trainer: null handle");
+  WVN_REQUIRE(method >= CONF_LATEST && method <= CONF_MOVING_AVERAGE, "trainer: confidence method %d (0 latest_measurement, "
+              "1 running_mean, 2 kalman_filter, 3 moving_average)", method);
+  ConfState& c = t->conf;
+  c.method = method;
+  c.running_n = running_n ? running_n : t->conf_priv;
+  c.running_sum = running_sum ? running_sum : t->conf_priv + 1;
+  c.running_sumsq = running_sumsq ? running_sumsq : t->conf_priv + 2;
+  c.var = var ? var : reinterpret_cast<float*>(t->conf_priv + 3);
+  c.kf_proc_cov = kf_proc_cov;
+  c.kf_meas_cov = kf_meas_cov;
+  c.ring = t->conf_priv + 4;
+  return WVN_OK;
 }
 
 int fused_comm_unique_id(void* id128) {
@@ -617,7 +722,7 @@ int fused_train_step(FusedTrainer* t, float* params, float* exp_avg, float* exp_
   const long long np = static_cast<long long>(t->o.total);
   NcclApi& api = nccl();
   if (phase_mask & 1) {
-    WVN_CHECK_CUDA(cudaMemsetAsync(t->sc, 0, sizeof(FusedScalars), stream));
+    WVN_CHECK_CUDA(cudaMemsetAsync(t->sc, 0, 6 * sizeof(double), stream));   // the sums; the extrema are reset by K4
     WVN_CHECK_CUDA(cudaMemsetAsync(t->grads, 0, sizeof(float) * (np + 1), stream));
     train_fwd_rows_kernel<<<tiles, kThreads, t->smem_fwd, stream>>>(s, t->o, params, x, y, y_valid, n_rows, groups, rpg,
                                                                    t->h1, t->h2, t->out, t->loss_reco, t->raw, t->sc);
@@ -625,12 +730,19 @@ int fused_train_step(FusedTrainer* t, float* params, float* exp_avg, float* exp_
     if (t->comm) {
       const int rc = api.AllReduce(t->sc, t->sc, 6, kNcclFloat64, kNcclSum, t->comm, stream);
       if (rc != 0) return set_error(WVN_ERR_CUDA, "ncclAllReduce(stats): %s", api.GetErrorString(rc));
+      if (t->conf.method == CONF_MOVING_AVERAGE) {
+        int r2 = api.AllReduce(&t->sc->x_min, &t->sc->x_min, 1, kNcclFloat64, kNcclMin, t->comm, stream);
+        if (r2 == 0) r2 = api.AllReduce(&t->sc->x_max, &t->sc->x_max, 1, kNcclFloat64, kNcclMax, t->comm, stream);
+        if (r2 != 0) return set_error(WVN_ERR_CUDA, "ncclAllReduce(extrema): %s", api.GetErrorString(r2));
+      }
     }
   }
   if (phase_mask & 2) {
+    train_conf_kernel<<<1, 32, 0, stream>>>(t->loss, t->conf, s.dim, t->sc, cg_mean, cg_std, step_counter);
+    WVN_CHECK_LAUNCH("train_conf_kernel");
     train_bwd_rows_kernel<<<tiles, kThreads, t->smem_bwd, stream>>>(
-        s, t->o, t->loss, params, x, y, y_valid, n_rows, groups, rpg, t->h1, t->h2, t->out, t->loss_reco, t->raw,
-        t->d_out, t->d_h2, t->d_h1, conf_out, t->sc, cg_mean, cg_std, t->grads + np, step_counter);
+        s, t->o, t->loss, t->conf.method, params, x, y, y_valid, n_rows, groups, rpg, t->h1, t->h2, t->out, t->loss_reco,
+        t->raw, t->d_out, t->d_h2, t->d_h1, conf_out, t->sc, t->grads + np);
     WVN_CHECK_LAUNCH("train_bwd_rows_kernel");
     WgradArgs w;
     const int n3 = s.dim + 1;

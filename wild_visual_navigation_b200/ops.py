@@ -394,6 +394,7 @@ class MlpTrainer:
         self.cg_std = torch.ones(1, device=dev)
         self.pg = process_group
         self.legacy = legacy
+        self._conf = None     # (method id, var, running_n, running_sum, running_sum_of_squares, kf_proc_cov, kf_meas_cov)
         self._h = None
         self._lib_comm = False
         if legacy:
@@ -413,6 +414,8 @@ class MlpTrainer:
         check(lib().wvn_mlp_trainer_create(self.dim, self.h1, self.h2, self.max_rows, byref(self.cfg), ptr(self.scalars),
                                            ptr(self.grads), byref(h)))
         self._h = h
+        if self._conf is not None:
+            self.set_confidence(*self._conf)
         self.conf = torch.empty(self.max_rows + 32, device=self.params.device, dtype=torch.float32)
         self._lib_comm = False
         if self.pg is not None:
@@ -429,6 +432,16 @@ class MlpTrainer:
                 raw = (ctypes.c_ubyte * 128)(*idt.cpu().tolist())
                 check(lib().wvn_mlp_trainer_init_comm(self._h, raw, rank, world))
                 self._lib_comm = True
+
+    def set_confidence(self, method=0, var=None, running_n=None, running_sum=None, running_sum_of_squares=None,
+                       kf_proc_cov=0.2, kf_meas_cov=1.0):
+        """ConfidenceGenerator method of the step (0 latest_measurement, 1 running_mean, 2 kalman_filter, 3
+        moving_average) and the device tensors holding its state (updated in place by the step; None = private)."""
+        assert not self.legacy or method == 0, "the round-1 kernels implement latest_measurement only"
+        self._conf = (int(method), var, running_n, running_sum, running_sum_of_squares, float(kf_proc_cov), float(kf_meas_cov))
+        if self._h is not None:
+            check(lib().wvn_mlp_trainer_set_confidence(self._h, int(method), ptr(var), ptr(running_n), ptr(running_sum),
+                                                       ptr(running_sum_of_squares), float(kf_proc_cov), float(kf_meas_cov)))
 
     def _run(self, x, groups, rpg, n_rows, y, yv):
         if groups * rpg > self.max_rows:
@@ -450,6 +463,9 @@ class MlpTrainer:
 
             phase(1)
             dist.all_reduce(self.scalars[:6], group=self.pg)
+            if self._conf is not None and self._conf[0] == 3:   # moving_average normalises by the global extrema
+                dist.all_reduce(self.scalars[6:7], op=dist.ReduceOp.MIN, group=self.pg)
+                dist.all_reduce(self.scalars[7:8], op=dist.ReduceOp.MAX, group=self.pg)
             phase(2)
             dist.all_reduce(self.grads, group=self.pg)
             phase(4)

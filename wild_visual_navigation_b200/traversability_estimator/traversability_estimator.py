@@ -107,9 +107,22 @@ class TraversabilityEstimator:
                                        anomaly_balanced=lp["anomaly_balanced"], lr=self._lr, process_group=process_group)
         # the train step writes the ConfidenceGenerator's mean / std straight into the module's parameters
         self._trainer.cg_mean, self._trainer.cg_std = cg.mean.data, cg.std.data
+        self._bind_confidence_state()
         self._loss = torch.tensor([torch.inf])
         self._step = 0
         self._last_confidence = None
+
+    def _bind_confidence_state(self):
+        """Points the fused step at the ConfidenceGenerator's own parameters (mean / std / var / running sums), so the
+        module's ``state_dict`` is always current without a copy or a host round trip."""
+        cg = self._traversability_loss._confidence_generator
+        kf = getattr(cg, "_kalman_filter", None)
+        self._trainer.cg_mean, self._trainer.cg_std = cg.mean.data, cg.std.data
+        self._trainer.set_confidence(
+            cg.method_id, cg.var.data, getattr(cg, "running_n", None), getattr(cg, "running_sum", None),
+            getattr(cg, "running_sum_of_squares", None),
+            kf_proc_cov=float(kf.proc_cov.item()) if kf is not None else 0.2,
+            kf_meas_cov=float(kf.meas_cov.item()) if kf is not None else 1.0)
 
     # ---- properties ------------------------------------------------------------------------
     @property
