@@ -245,6 +245,10 @@ int wvn_mlp_infer_set_params(wvn_mlp_infer_t* h, const float* params, void* stre
 int wvn_mlp_infer_pixels(wvn_mlp_infer_t* h, const float* tokens, int batch, int gh, int gw, int out_h, int out_w,
                          const float* cg_mean, const float* cg_std, float std_factor, float* trav, float* conf,
                          void* stream);
+/* The same maps straight from the backbone's own bf16 token buffer (the tokens of the last wvn_vit_forward* call, frames
+ * [0, batch)): no fp32 -> bf16 re-cast of the tokens.  Needs dim == the backbone's width and the fused geometry. */
+int wvn_mlp_infer_pixels_vit(wvn_mlp_infer_t* h, wvn_vit_t* vit, int batch, int out_h, int out_w, const float* cg_mean,
+                             const float* cg_std, float std_factor, float* trav, float* conf, void* stream);
 /* Same arithmetic on explicit rows x: [rows, dim] fp32 (segment-wise prediction mode). */
 int wvn_mlp_infer_rows(wvn_mlp_infer_t* h, const float* x, long long rows, const float* cg_mean,
                        const float* cg_std, float std_factor, float* trav, float* conf, void* stream);

@@ -108,3 +108,24 @@ def test_confidence_generator_state_dict_keys():
                                        "_confidence_generator.std"]
     x = torch.rand(10)
     assert torch.equal(cg.inference_without_update(x.to("meta")) if False else cg.inference_without_update(x), cg.inference_without_update(x))
+
+
+def test_product_weight_generators_match_the_oracles():
+    """The product must not import oracle/, so its seeded random-init generators (used when no checkpoint is given) are
+    written twice; this ties the two copies together bit for bit."""
+    import torch
+
+    from oracle.dino_vit import ViTConfig, synthetic_state_dict
+    from oracle.stego_head import synthetic_head
+    from wild_visual_navigation_b200.feature_extractor import weights
+
+    for name, patch, image in (("vit_small", 8, 224), ("vit_base", 8, 64)):
+        cfg = ViTConfig.from_name(name, patch, image)
+        for seed, attn_std in ((1, 0.09), (7, 0.2)):
+            want = synthetic_state_dict(cfg, seed=seed, attn_std=attn_std)
+            got = weights.synthetic_dino_state_dict(cfg.dim, cfg.depth, cfg.mlp_dim, patch, cfg.pretrain_grid, seed=seed,
+                                                    attn_std=attn_std)
+            assert list(got) == list(want)
+            assert all(torch.equal(got[k], want[k]) for k in want)
+    a, b = weights.synthetic_stego_head(384, 90, 32, 27, seed=3), synthetic_head(384, 90, 32, 27, seed=3)
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in b)

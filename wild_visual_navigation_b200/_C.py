@@ -74,6 +74,7 @@ SIGNATURES = {
     "wvn_mlp_infer_reserve": (_I, [_P, _I]),
     "wvn_mlp_infer_set_params": (_I, [_P, _P, _P]),
     "wvn_mlp_infer_pixels": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _P, _P, _P]),
+    "wvn_mlp_infer_pixels_vit": (_I, [_P, _P, _I, _I, _I, _P, _P, _F, _P, _P, _P]),
     "wvn_mlp_infer_rows": (_I, [_P, _P, _L, _P, _P, _F, _P, _P, _P]),
     "wvn_mlp_param_count": (_S, [_I, _I, _I]),
     "wvn_mlp_train_workspace_bytes": (_S, [_I, _I, _I, _I]),

@@ -814,6 +814,71 @@ int wvn_mlp_infer_set_params(wvn_mlp_infer_t* h, const float* params, void* stre
   return WVN_OK;
 }
 
+// Fused per-pixel head over frames [b0, b0 + nb): per-token GEMM (G | U | cT) + token Gram + one pixel kernel.
+// tok_bf16: the frames' bf16 tokens, frame_rows rows per frame with the patch tokens starting at row row0.
+static int pixels_fused_chunk(wvn_mlp_infer_t* h, const void* tok_bf16, long long frame_rows, int row0, int b0, int nb,
+                              int gh, int gw, int out_h, int out_w, int ww, const float* cg_mean, const float* cg_std,
+                              float std_factor, float* trav, float* conf, cudaStream_t s) {
+  const long long rows = static_cast<long long>(nb) * frame_rows;
+  GemmArgs g;
+  g.M = static_cast<int>(rows); g.N = kPixelHeadN; g.K = h->dim_p; g.epi = EPI_F32;
+  g.bias = reinterpret_cast<float*>(h->bias_cat.p); g.out = h->gu.p; g.ldo = kPixelHeadN;
+  WVN_PROPAGATE(gemm_bf16(g, tok_bf16, h->dim_p, h->wcat.p, 64, s));
+  WVN_PROPAGATE(token_gram(tok_bf16, reinterpret_cast<float*>(h->gram.p), nb, gh, gw, h->dim_p, frame_rows, row0, s));
+  PixelHeadArgs a;
+  a.gu = reinterpret_cast<float*>(h->gu.p); a.ldg = kPixelHeadN; a.gram = reinterpret_cast<float*>(h->gram.p);
+  a.consts = reinterpret_cast<PixelHeadConsts*>(h->head_consts.p);
+  a.cg_mean = cg_mean; a.cg_std = cg_std; a.std_factor = std_factor;
+  a.trav = trav + static_cast<long long>(b0) * out_h * out_w;
+  a.conf = conf + static_cast<long long>(b0) * out_h * out_w;
+  a.batch = nb; a.gh = gh; a.gw = gw; a.H = out_h; a.W = out_w;
+  a.sy = static_cast<float>(gh - 1) / static_cast<float>(out_h - 1);
+  a.sx = static_cast<float>(gw - 1) / static_cast<float>(out_w - 1);
+  a.ww = ww; a.feat = h->dim;
+  a.frame_rows = frame_rows; a.row0 = row0;
+#ifdef WVN_GEMM_TIMING
+  static long long* ptb = nullptr;
+  if (!ptb) cudaMalloc(&ptb, 16 * sizeof(long long));
+  a.timing = ptb;
+#endif
+  WVN_PROPAGATE(pixel_head(a, h->w2.p, h->h1_p, s));
+#ifdef WVN_GEMM_TIMING
+  {
+    long long t[16];
+    cudaMemcpyAsync(t, ptb, sizeof(t), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    const long long n = t[5] > 0 ? t[5] : 1;
+    fprintf(stderr, "[pixel_head timing, cycles per tile of CTA 0 (%lld tiles)] phaseA+sync %lld  phaseB+sync %lld  mma_wait %lld  "
+            "epilogue %lld  end_sync %lld | producer: tables+bar %lld  copy %lld  pix/gram %lld\n", n, t[0] / n, t[1] / n, t[2] / n, t[3] / n,
+            t[4] / n, t[8] / n, t[9] / n, t[10] / n);
+  }
+#endif
+  return WVN_OK;
+}
+
+int wvn_mlp_infer_pixels_vit(wvn_mlp_infer_t* h, wvn_vit_t* vit, int batch, int out_h, int out_w, const float* cg_mean,
+                             const float* cg_std, float std_factor, float* trav, float* conf, void* stream) {
+  WVN_REQUIRE(h && vit && trav && conf && cg_mean && cg_std, "wvn_mlp_infer_pixels_vit: null argument");
+  if (!h->loaded) return set_error(WVN_ERR_STATE, "wvn_mlp_infer_pixels_vit: parameters were never set");
+  if (!vit->forwarded || batch > vit->last_batch)
+    return set_error(WVN_ERR_STATE, "wvn_mlp_infer_pixels_vit: the backbone holds the tokens of %d frames, %d asked",
+                     vit->forwarded ? vit->last_batch : 0, batch);
+  WVN_REQUIRE(h->dim == vit->cfg.dim && h->dim_p == vit->cfg.dim, "wvn_mlp_infer_pixels_vit: the MLP takes %d-d features, "
+              "the backbone's tokens are %d-d", h->dim, vit->cfg.dim);
+  const int g = vit->grid;
+  const int ww = pixel_head_supported(h->h1, h->h2, g, g, out_h, out_w);
+  WVN_REQUIRE(ww > 0, "wvn_mlp_infer_pixels_vit: geometry outside the fused per-pixel head (use wvn_mlp_infer_pixels)");
+  if (h->fused_tokens < kFusedFrames * vit->npad) WVN_PROPAGATE(wvn_mlp_infer_reserve(h, vit->npad));
+  for (int b0 = 0; b0 < batch; b0 += kFusedFrames) {
+    const int nb = std::min(kFusedFrames, batch - b0);
+    const __nv_bfloat16* tok = reinterpret_cast<const __nv_bfloat16*>(vit->tok_bf16.p) +
+                               static_cast<long long>(b0) * vit->npad * vit->cfg.dim;
+    WVN_PROPAGATE(pixels_fused_chunk(h, tok, vit->npad, 1, b0, nb, g, g, out_h, out_w, ww, cg_mean, cg_std, std_factor, trav,
+                                     conf, S(stream)));
+  }
+  return WVN_OK;
+}
+
 int wvn_mlp_infer_pixels(wvn_mlp_infer_t* h, const float* tokens, int batch, int gh, int gw, int out_h, int out_w,
                          const float* cg_mean, const float* cg_std, float std_factor, float* trav, float* conf,
                          void* stream) {
@@ -836,38 +901,8 @@ int wvn_mlp_infer_pixels(wvn_mlp_infer_t* h, const float* tokens, int batch, int
       cast_rows_kernel<<<blocks, 256, 0, s>>>(tokens + static_cast<long long>(b0) * P * h->dim,
                                              reinterpret_cast<__nv_bfloat16*>(h->tok_bf16.p), rows, h->dim, h->dim_p);
       WVN_CHECK_LAUNCH("cast_rows_kernel");
-      GemmArgs g;
-      g.M = static_cast<int>(rows); g.N = kPixelHeadN; g.K = h->dim_p; g.epi = EPI_F32;
-      g.bias = reinterpret_cast<float*>(h->bias_cat.p); g.out = h->gu.p; g.ldo = kPixelHeadN;
-      WVN_PROPAGATE(gemm_bf16(g, h->tok_bf16.p, h->dim_p, h->wcat.p, 64, s));
-      WVN_PROPAGATE(token_gram(h->tok_bf16.p, reinterpret_cast<float*>(h->gram.p), nb, gh, gw, h->dim_p, s));
-      PixelHeadArgs a;
-      a.gu = reinterpret_cast<float*>(h->gu.p); a.ldg = kPixelHeadN; a.gram = reinterpret_cast<float*>(h->gram.p);
-      a.consts = reinterpret_cast<PixelHeadConsts*>(h->head_consts.p);
-      a.cg_mean = cg_mean; a.cg_std = cg_std; a.std_factor = std_factor;
-      a.trav = trav + static_cast<long long>(b0) * out_h * out_w;
-      a.conf = conf + static_cast<long long>(b0) * out_h * out_w;
-      a.batch = nb; a.gh = gh; a.gw = gw; a.H = out_h; a.W = out_w;
-      a.sy = static_cast<float>(gh - 1) / static_cast<float>(out_h - 1);
-      a.sx = static_cast<float>(gw - 1) / static_cast<float>(out_w - 1);
-      a.ww = ww; a.feat = h->dim;
-#ifdef WVN_GEMM_TIMING
-      static long long* ptb = nullptr;
-      if (!ptb) cudaMalloc(&ptb, 16 * sizeof(long long));
-      a.timing = ptb;
-#endif
-      WVN_PROPAGATE(pixel_head(a, h->w2.p, h->h1_p, s));
-#ifdef WVN_GEMM_TIMING
-      {
-        long long t[16];
-        cudaMemcpyAsync(t, ptb, sizeof(t), cudaMemcpyDeviceToHost, s);
-        cudaStreamSynchronize(s);
-        const long long n = t[5] > 0 ? t[5] : 1;
-        fprintf(stderr, "[pixel_head timing, cycles per tile of CTA 0 (%lld tiles)] phaseA+sync %lld  phaseB+sync %lld  mma_wait %lld  "
-                "epilogue %lld  end_sync %lld | producer: tables+bar %lld  copy %lld  pix/gram %lld\n", n, t[0] / n, t[1] / n, t[2] / n, t[3] / n,
-                t[4] / n, t[8] / n, t[9] / n, t[10] / n);
-      }
-#endif
+      WVN_PROPAGATE(pixels_fused_chunk(h, h->tok_bf16.p, P, 0, b0, nb, gh, gw, out_h, out_w, ww, cg_mean, cg_std,
+                                       std_factor, trav, conf, s));
     }
     return WVN_OK;
   }

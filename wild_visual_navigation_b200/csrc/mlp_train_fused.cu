@@ -55,7 +55,10 @@ train_fwd_rows_kernel(MlpShape s, MlpOffsets o, const float* __restrict__ params
                       const float* __restrict__ y, const unsigned char* __restrict__ y_valid,
                       const int* __restrict__ n_rows, int groups, int rpg, float* __restrict__ h1g,
                       float* __restrict__ h2g, float* __restrict__ outg, float* __restrict__ loss_reco,
-                      float* __restrict__ raw, FusedScalars* __restrict__ sc) {
+                      float* __restrict__ raw, FusedScalars* __restrict__ sc, float* __restrict__ trav_w_sum) {
+  // the confidence-weighted traversability sum of this step is accumulated by K2: start it from zero here (the flat
+  // gradient itself is cleared by K2 before K3 accumulates into it, the statistic sums by the previous step's K4)
+  if (blockIdx.x == 0 && threadIdx.x == 0) *trav_w_sum = 0.f;
   extern __shared__ __align__(16) float sm[];
   const int dim = s.dim, h1 = s.h1, h2 = s.h2, n3 = s.dim + 1;
   float* xt = sm;                               // [dim][TR]
@@ -320,7 +323,9 @@ __device__ __forceinline__ float row_confidence(int method, float lr, float lo, 
 }
 
 // ------------------------------------------------------------------------------------------------ K2
-// smem (floats): dot[n3][TRP] | dh2t[h2][TR] | rowinfo[TR]
+// smem (floats): dot[n3][TRP] | dh2t[h2][TR] | rowinfo[TR] | cst[8]
+// conf_method == CONF_LATEST: the generator's update has no memory, so every block derives it from the sums itself
+// (block 0 publishes it and bumps the step counter) and train_conf_kernel is not launched: the default step is 4 launches.
 __global__ void __launch_bounds__(kThreads)
 train_bwd_rows_kernel(MlpShape s, MlpOffsets o, LossCfg cfg, int conf_method, const float* __restrict__ params,
                       const float* __restrict__ x, const float* __restrict__ y,
@@ -328,7 +333,12 @@ train_bwd_rows_kernel(MlpShape s, MlpOffsets o, LossCfg cfg, int conf_method, co
                       const float* __restrict__ h1g, const float* __restrict__ h2g, const float* __restrict__ outg,
                       const float* __restrict__ loss_reco, const float* __restrict__ raw, float* __restrict__ d_out,
                       float* __restrict__ d_h2, float* __restrict__ d_h1, float* __restrict__ conf_out,
-                      const FusedScalars* __restrict__ sc, float* __restrict__ trav_w_sum) {
+                      FusedScalars* __restrict__ sc, float* __restrict__ cg_mean, float* __restrict__ cg_std,
+                      float* __restrict__ trav_w_sum, long long* __restrict__ step_counter,
+                      float* __restrict__ grads_clear, long long n_clear) {
+  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < n_clear;
+       i += static_cast<long long>(gridDim.x) * kThreads)
+    grads_clear[i] = 0.f;   // K3 accumulates the weight gradients with atomics
   extern __shared__ __align__(16) float sm[];
   const int dim = s.dim, h1 = s.h1, h2 = s.h2, n3 = s.dim + 1;
   float* dot = sm;                                 // [n3][TRP]
@@ -336,9 +346,35 @@ train_bwd_rows_kernel(MlpShape s, MlpOffsets o, LossCfg cfg, int conf_method, co
   int* rinfo = reinterpret_cast<int*>(dh2t + h2 * TR);
   const int t = threadIdx.x;
   const int r0 = blockIdx.x * TR;
+  float* cst = reinterpret_cast<float*>(rinfo + TR);  // lo, hi, g_reco, g_trav
   if (t < TR) rinfo[t] = compact_index(n_rows, groups, rpg, r0 + t);
+  if (t == 0) {
+    if (conf_method == CONF_LATEST) {
+      // ConfidenceGenerator.update_latest_measurement (confidence_generator.py:78-82) from the (all-reduced) sums
+      const double n = sc->n_valid;
+      const double mean = sc->sum_lr / n;                                  // n == 0 -> NaN, like torch's mean of empty
+      const double var = (sc->sum_lr2 - n * mean * mean) / (n - 1.0);     // n == 1 -> NaN, like torch.std
+      const float m = static_cast<float>(mean);
+      const float sd = (n > 1.0) ? static_cast<float>(sqrt(fmax(var, 0.0))) : nanf("");
+      const float shifted = m + sd * cfg.std_factor;
+      cst[0] = fmaxf(shifted - sd, 0.f);
+      cst[1] = shifted + sd;
+      cst[2] = cfg.w_reco * 2.f / (static_cast<float>(n) * static_cast<float>(dim));
+      cst[3] = cfg.w_trav * 2.f / static_cast<float>(sc->n_rows);
+      cst[4] = cst[5] = 0.f;
+      if (blockIdx.x == 0) {
+        sc->mean = m;
+        sc->std = sd;
+        if (cg_mean) *cg_mean = m;
+        if (cg_std) *cg_std = sd;
+        *step_counter += 1;  // torch.optim.Adam counts from 1; K4 reads the bumped value
+      }
+    } else {
+      cst[0] = sc->lo; cst[1] = sc->hi; cst[2] = sc->g_reco; cst[3] = sc->g_trav; cst[4] = sc->cmin; cst[5] = sc->cmax;
+    }
+  }
   __syncthreads();
-  const float lo = sc->lo, hi = sc->hi, cmin = sc->cmin, cmax = sc->cmax, g_reco = sc->g_reco, g_trav = sc->g_trav;
+  const float lo = cst[0], hi = cst[1], g_reco = cst[2], g_trav = cst[3], cmin = cst[4], cmax = cst[5];
   // ---- dOut (one warp per 4 rows), kept transposed in shared memory for the two products below
   {
     const int warp = t >> 5, lane = t & 31;
@@ -532,8 +568,10 @@ train_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
       metrics[0] = sc->loss_total; metrics[1] = sc->loss_trav; metrics[2] = sc->loss_reco;
       metrics[3] = sc->loss_trav_conf; metrics[4] = sc->mean; metrics[5] = sc->std;
     }
-    sc->x_min = __longlong_as_double(0x7ff0000000000000ll);   // +inf / 0: ready for the next step's atomicMin / atomicMax
+    // leave the accumulators clean for the next step (no memsets on the per-frame path)
+    sc->x_min = __longlong_as_double(0x7ff0000000000000ll);   // +inf / 0: ready for atomicMin / atomicMax
     sc->x_max = 0.0;
+    sc->sum_lr = sc->sum_lr2 = sc->sum_raw = sc->n_valid = sc->n_rows = sc->reserved = 0.0;
   }
   // torch.optim.Adam (no amsgrad, no weight decay): step t counts from 1
   const double t = static_cast<double>(*step_ptr);
@@ -722,10 +760,10 @@ int fused_train_step(FusedTrainer* t, float* params, float* exp_avg, float* exp_
   const long long np = static_cast<long long>(t->o.total);
   NcclApi& api = nccl();
   if (phase_mask & 1) {
-    WVN_CHECK_CUDA(cudaMemsetAsync(t->sc, 0, 6 * sizeof(double), stream));   // the sums; the extrema are reset by K4
-    WVN_CHECK_CUDA(cudaMemsetAsync(t->grads, 0, sizeof(float) * (np + 1), stream));
+    // no memsets: the statistic sums were left clean by the previous step's K4 (by create for the first step)
     train_fwd_rows_kernel<<<tiles, kThreads, t->smem_fwd, stream>>>(s, t->o, params, x, y, y_valid, n_rows, groups, rpg,
-                                                                   t->h1, t->h2, t->out, t->loss_reco, t->raw, t->sc);
+                                                                   t->h1, t->h2, t->out, t->loss_reco, t->raw, t->sc,
+                                                                   t->grads + np);
     WVN_CHECK_LAUNCH("train_fwd_rows_kernel");
     if (t->comm) {
       const int rc = api.AllReduce(t->sc, t->sc, 6, kNcclFloat64, kNcclSum, t->comm, stream);
@@ -738,11 +776,13 @@ int fused_train_step(FusedTrainer* t, float* params, float* exp_avg, float* exp_
     }
   }
   if (phase_mask & 2) {
-    train_conf_kernel<<<1, 32, 0, stream>>>(t->loss, t->conf, s.dim, t->sc, cg_mean, cg_std, step_counter);
-    WVN_CHECK_LAUNCH("train_conf_kernel");
+    if (t->conf.method != CONF_LATEST) {   // generators with memory: one thread updates the state once
+      train_conf_kernel<<<1, 32, 0, stream>>>(t->loss, t->conf, s.dim, t->sc, cg_mean, cg_std, step_counter);
+      WVN_CHECK_LAUNCH("train_conf_kernel");
+    }
     train_bwd_rows_kernel<<<tiles, kThreads, t->smem_bwd, stream>>>(
         s, t->o, t->loss, t->conf.method, params, x, y, y_valid, n_rows, groups, rpg, t->h1, t->h2, t->out, t->loss_reco,
-        t->raw, t->d_out, t->d_h2, t->d_h1, conf_out, t->sc, t->grads + np);
+        t->raw, t->d_out, t->d_h2, t->d_h1, conf_out, t->sc, cg_mean, cg_std, t->grads + np, step_counter, t->grads, np);
     WVN_CHECK_LAUNCH("train_bwd_rows_kernel");
     WgradArgs w;
     const int n3 = s.dim + 1;

@@ -132,7 +132,7 @@ pixel_head_kernel(const __grid_constant__ CUtensorMap tmap_w2, const PixelHeadAr
   auto phase_a = [&](const TileGeo& g) {
     const int t = threadIdx.x - 128;  // 0..127
     WVN_PP0
-    const float* gub = a.gu + static_cast<long long>(g.b) * P * a.ldg;
+    const float* gub = a.gu + (static_cast<long long>(g.b) * (a.frame_rows ? a.frame_rows : P) + a.row0) * a.ldg;
     int y0r[kTileH], y1r[kTileH];
     float wyr[kTileH];
 #pragma unroll
@@ -201,7 +201,7 @@ pixel_head_kernel(const __grid_constant__ CUtensorMap tmap_w2, const PixelHeadAr
       const bool same_y = (y0r[r] + 1 > a.gh - 1);
       const int tc = min(g.cx0 + c, a.gw - 1);
       const bool same_x = (tc + 1 > a.gw - 1);
-      const float* gr = a.gram + static_cast<long long>(g.b) * P * 5;
+      const float* gr = a.gram + (static_cast<long long>(g.b) * (a.frame_rows ? a.frame_rows : P) + a.row0) * 5;
       const float* e0 = gr + (static_cast<long long>(y0r[r]) * a.gw + tc) * 5;
       const float* e1 = gr + (static_cast<long long>(y1r[r]) * a.gw + tc) * 5;
       const float s00 = __ldg(e0), h0 = __ldg(e0 + 1), v0r = __ldg(e0 + 2), dr = __ldg(e0 + 3), anr = __ldg(e0 + 4);
@@ -367,7 +367,8 @@ pixel_head_kernel(const __grid_constant__ CUtensorMap tmap_w2, const PixelHeadAr
 
 // One warp per token: self / right / lower / lower-right / (right . lower) dot products (bf16 tokens).
 __global__ void __launch_bounds__(256)
-token_gram_kernel(const __nv_bfloat16* __restrict__ tok, float* __restrict__ gram, int batch, int gh, int gw, int dim) {
+token_gram_kernel(const __nv_bfloat16* __restrict__ tok, float* __restrict__ gram, int batch, int gh, int gw, int dim,
+                  long long frame_rows, int row0) {
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -375,7 +376,8 @@ token_gram_kernel(const __nv_bfloat16* __restrict__ tok, float* __restrict__ gra
   for (long long t = warp_global; t < batch * P; t += warps_total) {
     const int x = static_cast<int>(t % gw), y = static_cast<int>((t / gw) % gh);
     const bool has_r = x + 1 < gw, has_d = y + 1 < gh;
-    const __nv_bfloat16* p00 = tok + t * dim;
+    const long long row = (t / P) * frame_rows + row0 + (t % P);   // token t of the batch in the (possibly padded) buffer
+    const __nv_bfloat16* p00 = tok + row * dim;
     const __nv_bfloat16* p01 = has_r ? p00 + dim : p00;
     const __nv_bfloat16* p10 = has_d ? p00 + static_cast<long long>(gw) * dim : p00;
     const __nv_bfloat16* p11 = p10 + (has_r ? dim : 0);
@@ -393,7 +395,7 @@ token_gram_kernel(const __nv_bfloat16* __restrict__ tok, float* __restrict__ gra
     }
     s = warp_sum(s); h = warp_sum(h); v = warp_sum(v); d = warp_sum(d); an = warp_sum(an);
     if (lane == 0) {
-      float* g = gram + t * 5;
+      float* g = gram + row * 5;
       g[0] = s; g[1] = h; g[2] = v; g[3] = d; g[4] = an;
     }
   }
@@ -468,11 +470,14 @@ int pixel_head_pack(const float* params, const MlpShape& s, int dim_p, void* wca
   return WVN_OK;
 }
 
-int token_gram(const void* tok_bf16, float* gram, int batch, int gh, int gw, int dim, cudaStream_t stream) {
+int token_gram(const void* tok_bf16, float* gram, int batch, int gh, int gw, int dim, long long frame_rows, int row0,
+               cudaStream_t stream) {
+  if (frame_rows <= 0) frame_rows = static_cast<long long>(gh) * gw;
   WVN_REQUIRE(dim % 64 == 0, "token_gram: dim %d must be a multiple of 64", dim);
   const long long warps = static_cast<long long>(batch) * gh * gw;
   int blocks = static_cast<int>(std::min<long long>((warps * 32 + 255) / 256, static_cast<long long>(sm_count()) * 16));
-  token_gram_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(tok_bf16), gram, batch, gh, gw, dim);
+  token_gram_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(tok_bf16), gram, batch, gh, gw, dim,
+                                                frame_rows, row0);
   WVN_CHECK_LAUNCH("token_gram_kernel");
   return WVN_OK;
 }

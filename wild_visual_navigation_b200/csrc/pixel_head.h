@@ -35,6 +35,8 @@ struct PixelHeadArgs {
   float sy = 0.f, sx = 0.f;      // (gh-1)/(H-1), (gw-1)/(W-1)
   int ww = 0;                    // token-window columns per tile (from pixel_head_supported)
   int feat = 0;                  // D
+  long long frame_rows = 0;      // rows of gu / gram between two frames (0 = gh*gw): the ViT's own token buffer keeps
+  int row0 = 0;                  // npad rows per frame with the patch tokens starting at row 1
   long long* timing = nullptr;   // debug (-DWVN_GEMM_TIMING builds): phase cycle counters of CTA 0
 };
 
@@ -42,7 +44,8 @@ struct PixelHeadArgs {
 int pixel_head_supported(int h1, int h2, int gh, int gw, int H, int W);
 int pixel_head_pack(const float* params, const MlpShape& s, int dim_p, void* wcat_bf16, float* bias,
                     PixelHeadConsts* consts, cudaStream_t stream);
-int token_gram(const void* tok_bf16, float* gram, int batch, int gh, int gw, int dim, cudaStream_t stream);
+int token_gram(const void* tok_bf16, float* gram, int batch, int gh, int gw, int dim, long long frame_rows, int row0,
+               cudaStream_t stream);
 int pixel_head(const PixelHeadArgs& a, const void* w2_bf16, int w2_ld, cudaStream_t stream);
 
 }  // namespace wvn

@@ -26,7 +26,7 @@ class TraversabilityInference:
         self._model = model
         self._cg = confidence_generator
         self._mlp = ops.MlpInference(model.input_size, model.hidden[0], model.hidden[1], chunk_rows,
-                                       tokens_per_frame=dino.grid * dino.grid)
+                                       tokens_per_frame=max(dino.grid * dino.grid, getattr(dino._model, "npad", 0)))
         self.refresh_weights()
 
     def refresh_weights(self):
@@ -53,6 +53,13 @@ class TraversabilityInference:
     @torch.no_grad()
     def predict_from_tokens(self, tokens: torch.Tensor, out_size: int):
         g = self._dino.grid
+        vit = self._dino._model
+        last = getattr(vit, "last_tokens", None)
+        if (last is not None and tokens.data_ptr() == last.data_ptr() and tokens.shape[1:] == last.shape[1:]
+                and tokens.shape[0] <= last.shape[0] and self._model.input_size == vit.dim and out_size % 64 == 0):
+            # these ARE the backbone's last tokens: its bf16 copy goes to the head as it is (no re-cast of 4.8 MB/frame)
+            return self._mlp.pixels_from_vit(vit, tokens.shape[0], (out_size, out_size), self._cg.mean.data,
+                                             self._cg.std.data, self._cg.std_factor)
         return self._mlp.pixels(tokens, (g, g), (out_size, out_size), self._cg.mean.data, self._cg.std.data,
                                 self._cg.std_factor)
 

@@ -289,6 +289,7 @@ class ViTBackbone:
             resized_hw = _resized_size(H, W, self.image_size)
         tokens = torch.empty(2 * B if flip_tta else B, self.P, self.dim, device=img.device, dtype=torch.float32)
         check(fn(self._h, ptr(img), B, H, W, resized_hw[0], resized_hw[1], ptr(tokens), stream()))
+        self.last_tokens = tokens   # the handle's bf16 copy of exactly these tokens feeds the per-pixel head directly
         return tokens
 
     def stego_head(self, batch: int) -> torch.Tensor:
@@ -335,6 +336,14 @@ class MlpInference:
         conf = torch.empty_like(trav)
         check(lib().wvn_mlp_infer_pixels(self._h, ptr(tokens), B, grid[0], grid[1], out_hw[0], out_hw[1], ptr(cg_mean),
                                          ptr(cg_std), float(std_factor), ptr(trav), ptr(conf), stream()))
+        return trav, conf
+
+    def pixels_from_vit(self, vit: "ViTBackbone", batch, out_hw, cg_mean, cg_std, std_factor):
+        """The same maps from the backbone's own bf16 tokens of its last forward (frames [0, batch))."""
+        trav = torch.empty(batch, out_hw[0], out_hw[1], device=cg_mean.device, dtype=torch.float32)
+        conf = torch.empty_like(trav)
+        check(lib().wvn_mlp_infer_pixels_vit(self._h, vit._h, batch, out_hw[0], out_hw[1], ptr(cg_mean), ptr(cg_std),
+                                             float(std_factor), ptr(trav), ptr(conf), stream()))
         return trav, conf
 
     def rows(self, x, cg_mean, cg_std, std_factor):
