@@ -11,8 +11,14 @@
 // in the head buffer's cluster-logit columns and the existing upsample+argmax kernel (dense_kernels.cu) produces the
 // pixel labels — the (H, W, 90) tensor is never formed.
 //
-// ONE launch runs all iterations for the whole batch: a thread-block CLUSTER of 8 CTAs owns a frame (8 x 392 of the
-// 3136 patches at 448 px), so a batch of 32 frames fills the GPU instead of 32 SMs.  The CTA's code rows are staged in
+// ONE launch runs all iterations for the whole batch: a TEAM of 9 CTAs owns a frame (9 x 349 of the 3136 patches at
+// 448 px), so a batch of 32 frames fills the GPU instead of 32 SMs (16 teams = 144 of 148 SMs: two full rounds).  The team synchronises once per iteration through a
+// per-frame arrival counter in global memory (release / acquire); the partial sums travel through global memory anyway.
+// Round 2 first used hardware thread-block clusters for the team: a cluster of 8 one-CTA-per-SM blocks must sit inside one
+// GPC and fits only 15 times on a B200 (120 of 148 SMs), so 32 frames took THREE rounds with the last almost empty
+// (750 us); free CTAs of 9 fit 16 teams at a time: two full rounds (445 us).  CTAs are dispatched in block order, so a team split by the
+// residency boundary only waits for earlier teams to retire (no circular wait); the spin is bounded and traps.
+// The CTA's code rows are staged in
 // shared memory ONCE (coalesced; the first version re-read them from L2 every pass with one row per lane — with the
 // shared-memory carve-out at its maximum there is no L1 left, and those 32-sector requests made the kernel 1.4 ms).
 // Per iteration and CTA:
@@ -32,7 +38,29 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kCluster = 8;
+constexpr int kCluster = 9;   // CTAs per frame (a software team, see above): 16 teams = 144 SMs, 32 frames = 2 full rounds
+
+// Arrive at the frame's counter and wait until `target` arrivals: release before, acquire after; bounded (traps after
+// ~2 s instead of hanging the GPU if a team member never shows up).
+__device__ __forceinline__ void team_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    unsigned int v;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= target) break;
+      __nanosleep(64);
+      if (clock64() - t0 > 4000000000ll) {
+        printf("[wvn] stego_kmeans: team barrier timed out (block %d, %u of %u)\n", blockIdx.x, v, target);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
 constexpr int kMaxK = 64;
 constexpr int kMaxC = 128;   // code_dim <= 128 (row registers: 128)
 
@@ -57,7 +85,7 @@ stego_kmeans_kernel(float* __restrict__ rows, KmeansArgs a, float* __restrict__ 
   float* rows_s = sum_priv + n_priv * K * CP;  // [per][C + 1] (odd row stride: one row per lane is conflict-free)
   __shared__ unsigned char assign[1024];       // per CTA: <= 1024 patches (8 CTAs per frame)
 
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = blockIdx.x % kCluster;
   const int frame = blockIdx.x / kCluster;
   const int per = (P + kCluster - 1) / kCluster;
   const int p0 = rank * per, p1 = min(P, p0 + per);
@@ -184,7 +212,7 @@ stego_kmeans_kernel(float* __restrict__ rows, KmeansArgs a, float* __restrict__ 
     }
     __syncthreads();
     WVN_KT(3)
-    // ---- 3. CTA partial -> global; cluster barrier; every CTA sums the 8 partials in rank order
+    // ---- 3. CTA partial -> global; team barrier; every CTA sums the team's partials in rank order
     float* mine = part_frame + ((it & 1) * kCluster + rank) * (K * CP + K);
     for (int i = t; i < K * CP + K; i += kThreads) {
       float sacc = 0.f;
@@ -195,9 +223,8 @@ stego_kmeans_kernel(float* __restrict__ rows, KmeansArgs a, float* __restrict__ 
       }
       mine[i] = sacc;
     }
-    __threadfence();
     WVN_KT(4)
-    cluster_sync_all();
+    team_barrier(a.frame_bar + frame, static_cast<unsigned int>(kCluster) * (it + 1));
     WVN_KT(5)
     const float* all = part_frame + (it & 1) * kCluster * (K * CP + K);
     for (int k = warp; k < K; k += kWarps) {  // one warp per centroid
@@ -232,7 +259,8 @@ stego_kmeans_kernel(float* __restrict__ rows, KmeansArgs a, float* __restrict__ 
 
 size_t stego_kmeans_workspace_bytes(int batch, int k, int code_dim) {
   const int CP = code_dim <= 96 ? 96 : 128;
-  return sizeof(float) * static_cast<size_t>(batch) * 2 * kCluster * (static_cast<size_t>(k) * CP + k);
+  return sizeof(float) * static_cast<size_t>(batch) * 2 * kCluster * (static_cast<size_t>(k) * CP + k) +
+         sizeof(unsigned int) * static_cast<size_t>(batch) + 16;
 }
 
 int stego_kmeans(float* rows, const KmeansArgs& a_in, float* workspace, cudaStream_t stream) {
@@ -260,24 +288,16 @@ int stego_kmeans(float* rows, const KmeansArgs& a_in, float* workspace, cudaStre
   auto kern = a.code_dim <= 96 ? (a.rows_in_smem ? stego_kmeans_kernel<96, true> : stego_kmeans_kernel<96, false>)
                                : (a.rows_in_smem ? stego_kmeans_kernel<128, true> : stego_kmeans_kernel<128, false>);
   WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(a.batch * kCluster);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  // the per-frame arrival counters live behind the partial sums and start from zero
+  const size_t part_floats = static_cast<size_t>(a.batch) * 2 * kCluster * (static_cast<size_t>(a.k) * CP + a.k);
+  a.frame_bar = reinterpret_cast<unsigned int*>(workspace + ((part_floats + 3) & ~static_cast<size_t>(3)));
+  WVN_CHECK_CUDA(cudaMemsetAsync(a.frame_bar, 0, sizeof(unsigned int) * a.batch, stream));
 #ifdef WVN_GEMM_TIMING
   static long long* tbuf = nullptr;
   if (!tbuf) cudaMalloc(&tbuf, 8 * sizeof(long long));
   a.timing = tbuf;
 #endif
-  WVN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, rows, a, workspace));
+  kern<<<a.batch * kCluster, kThreads, smem, stream>>>(rows, a, workspace);
   WVN_CHECK_LAUNCH("stego_kmeans_kernel");
 #ifdef WVN_GEMM_TIMING
   {
