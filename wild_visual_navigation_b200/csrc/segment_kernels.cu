@@ -370,15 +370,23 @@ adjacency_emit_kernel(const unsigned int* __restrict__ adj, long long* __restric
 }
 
 // ---- relabel: compact the set of labels present in a frame to 0..S-1 (sorted order)
+// grid = (slices per frame, batch): the labels a block meets are collected in a shared-memory flag array first — letting
+// every pixel store its flag to global memory made 6.4 M stores hit ~640 addresses (75 us per 32 frames)
 __global__ void __launch_bounds__(256)
-label_presence_kernel(const long long* __restrict__ seg, int* __restrict__ present, int batch, long long pix_per_frame,
-                      int num_labels) {
-  const long long total = batch * pix_per_frame;
-  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long v = seg[p];
-    if (v >= 0 && v < num_labels) present[(p / pix_per_frame) * num_labels + v] = 1;
+label_presence_kernel(const long long* __restrict__ seg, int* __restrict__ present, long long pix_per_frame, int num_labels) {
+  extern __shared__ int flags[];
+  for (int i = threadIdx.x; i < num_labels; i += blockDim.x) flags[i] = 0;
+  __syncthreads();
+  const long long per = (pix_per_frame + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per, p1 = min(pix_per_frame, p0 + per);
+  const long long* fr = seg + blockIdx.y * pix_per_frame;
+  for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+    const long long v = fr[p];
+    if (v >= 0 && v < num_labels && flags[v] == 0) flags[v] = 1;   // benign race: every writer stores 1
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < num_labels; i += blockDim.x)
+    if (flags[i]) present[static_cast<long long>(blockIdx.y) * num_labels + i] = 1;
 }
 
 __global__ void label_scan_kernel(int* __restrict__ present, int* __restrict__ counts, int num_labels) {
@@ -541,7 +549,8 @@ int relabel_compact(long long* seg, int* scratch, int* counts, int batch, long l
   long long blocks = (total + 255) / 256;
   const long long max_blocks = static_cast<long long>(sm_count()) * 16;
   if (blocks > max_blocks) blocks = max_blocks;
-  label_presence_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(seg, scratch, batch, pix_per_frame, num_labels);
+  const int slices = static_cast<int>(std::min<long long>((pix_per_frame + 4095) / 4096, 32));
+  label_presence_kernel<<<dim3(slices, batch), 256, sizeof(int) * num_labels, stream>>>(seg, scratch, pix_per_frame, num_labels);
   WVN_CHECK_LAUNCH("label_presence_kernel");
   label_scan_kernel<<<batch, 1, 0, stream>>>(scratch, counts, num_labels);
   WVN_CHECK_LAUNCH("label_scan_kernel");
