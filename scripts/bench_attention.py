@@ -12,8 +12,9 @@ from wild_visual_navigation_b200 import ops  # noqa: E402
 B, H, N = int(os.environ.get("B", 8)), 6, 3137
 npad = (N + 127) // 128 * 128
 g = torch.Generator(device="cuda").manual_seed(0)
-q = (torch.randn(B, H, npad, 64, device="cuda", generator=g) * 1.2).bfloat16()
-k = (torch.randn(B, H, npad, 64, device="cuda", generator=g) * 1.2).bfloat16()
+S = float(os.environ.get("QK_STD", 1.2))   # std of q and k: the logits have std S^2 (1.2: bland; 1.8: the bench ViT's spread)
+q = (torch.randn(B, H, npad, 64, device="cuda", generator=g) * S).bfloat16()
+k = (torch.randn(B, H, npad, 64, device="cuda", generator=g) * S).bfloat16()
 v = torch.randn(B, H, npad, 64, device="cuda", generator=g).bfloat16()
 vt = v.transpose(2, 3).contiguous()
 out = ops.attention(q, k, vt, N, 0.125)

@@ -1252,7 +1252,7 @@ constexpr int kWarpTma = 4, kWarpMma = 5;
 
 struct SoftmaxCtx5 {
   uint32_t tmem_s, tmem_o;
-  float sl2;
+  float sl2, thr;
   uint64_t *s_full, *p_full;
   float m_ref, l;
 };
@@ -1307,7 +1307,7 @@ __device__ __forceinline__ void softmax_tile5(SoftmaxCtx5& c, int j, int valid, 
     c.m_ref = mx;
   } else {
     const float m_new = fmaxf(c.m_ref, mx);
-    const bool need = (m_new - c.m_ref) * c.sl2 > kRescaleThreshold;
+    const bool need = (m_new - c.m_ref) * c.sl2 > c.thr;
     if (__any_sync(0xffffffffu, need)) {   // O is quiescent: see the wait above
       const float alpha = need ? fast_exp2((c.m_ref - m_new) * c.sl2) : 1.f;
       if (need) c.m_ref = m_new;
@@ -1504,6 +1504,7 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     c.tmem_s = tmem_base + lane_base + v5::kColS;
     c.tmem_o = tmem_base + lane_base + v5::kColO;
     c.sl2 = args.scale_log2;
+    c.thr = args.rescale_log2;
     c.s_full = s_full;
     c.p_full = p_full;
     c.m_ref = -INFINITY;
@@ -1591,8 +1592,15 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
     const char* e = getenv("WVN_ATTN_TOKEN");
     no_token = (e && atoi(e) == 0) ? 1 : 0;
   }
+  static float rescale = -1.f;  // $WVN_ATTN_RESCALE: lazy-rescale threshold in log2 units (impl 5)
+  if (rescale < 0.f) {
+    const char* e = getenv("WVN_ATTN_RESCALE");
+    rescale = e ? static_cast<float>(atof(e)) : a.rescale_log2;
+    if (!(rescale >= 0.f && rescale <= 64.f)) rescale = a.rescale_log2;
+  }
   AttnArgs a2 = a;
   a2.no_token = no_token;
+  a2.rescale_log2 = rescale;
   const int ntiles = a.npad / kTileQ;
   dim3 grid(impl == 2 ? (ntiles + 1) / 2 : ntiles, static_cast<unsigned>(bh));
   const bool four = impl == 5;
