@@ -197,12 +197,15 @@ class ConfidenceState:
 
     def update(self, x: torch.Tensor, xp: torch.Tensor) -> torch.Tensor:
         x, xp = x.detach(), xp.detach()
+        if self.mean.device != x.device:   # the state follows the data (the GPU-eager leg of bench.py runs on cuda)
+            self.mean, self.var, self.std = self.mean.to(x.device), self.var.to(x.device), self.std.to(x.device)
+            self.running = self.running.to(x.device)
         m = self.method
         if m == "latest_measurement":
             self.mean[0], self.std[0] = xp.mean(), xp.std()
             return confidence_inference(x, self.mean, self.std, self.std_factor)
         if m == "running_mean":
-            self.running += torch.stack([torch.tensor(float(xp.numel()), dtype=torch.float64), xp.sum().double(),
+            self.running += torch.stack([torch.tensor(float(xp.numel()), dtype=torch.float64, device=x.device), xp.sum().double(),
                                          (xp ** 2).sum().double()])
             self.mean[0] = self.running[1] / self.running[0]
             self.var[0] = self.running[2:3] / self.running[0] - self.mean ** 2     # float64 - float32 -> float64 -> float32

@@ -319,3 +319,13 @@ def test_estimator_loads_reference_made_checkpoint(golden_dir, tmp_path):
     ck2 = torch.load(os.path.join(tmp_path, "ck.pt"), weights_only=False)
     assert list(ck2["traversability_loss_state_dict"]) == list(ck["traversability_loss_state_dict"])
     assert list(ck2["model_state_dict"]) == list(ck["model_state_dict"])
+
+
+def test_bench_eager_and_cpu_legs_run():
+    """bench.py's comparison legs (the oracle port as eager fp32 PyTorch on the GPU, with and without SDPA, and on the CPU)
+    must keep running when the oracle changes: one small step of each."""
+    import bench
+
+    for device, sdpa in (("cuda", False), ("cuda", True)):
+        fps, ms = bench.oracle_frames_per_s("c3", 1, 1, 0, device, sdpa=sdpa)
+        assert fps > 0 and ms > 0
