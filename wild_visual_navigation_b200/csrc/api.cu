@@ -192,7 +192,7 @@ int wvn_attention_bf16(const void* q, const void* k, const void* vt, void* out, 
               "mma: issue_qk(+waits) %lld  wait_p %lld  wait_v+issue_pv %lld  loop %lld\n",
               timing_buf[0] / nkv, timing_buf[1] / nkv, timing_buf[2] / nkv, timing_buf[3] / nkv, timing_buf[4] / nkv,
               timing_buf[8] / nkv, timing_buf[9] / nkv, timing_buf[10] / nkv, timing_buf[11] / nkv);
-    else if (impl == nullptr || atoi(impl) == 5 || atoi(impl) == 7)
+    else if (impl == nullptr || atoi(impl) == 5)
       fprintf(stderr, "[attn v5 timing, cycles per 64-key tile, thread 0] wait_s %lld  ldtm %lld  max+rescale %lld  exp %lld  store %lld\n",
               timing_buf[0] / ((n_valid + 63) / 64), timing_buf[1] / ((n_valid + 63) / 64), timing_buf[2] / ((n_valid + 63) / 64),
               timing_buf[3] / ((n_valid + 63) / 64), timing_buf[4] / ((n_valid + 63) / 64));

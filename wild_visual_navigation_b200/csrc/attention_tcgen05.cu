@@ -1558,348 +1558,6 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   }
 }
 
-// =====================================================================================================================
-// v7 (round 2): THREE co-resident CTAs per SM with P in its own tensor-memory columns.
-//
-// v5's softmax threads wait ~900 of ~2450 clk per tile for S(j+1): with P written over S, Q·K^T(j+1) can only be queued
-// behind P·V(j).  Tensor memory is allocated in powers of two, but a CTA may allocate twice: 128 columns (S 64 | O 64)
-// + 32 columns (P) = 160, which fits three times into the SM's 512.  Q·K^T(j+1) is then issued as soon as the scores of
-// tile j are in registers (v1's early issue) and runs under the exponentials: a shorter chain per CTA, three chains per
-// SM instead of four.  64-key tiles, TMA / smem layout and the one-thread-per-row softmax are v5's; the dynamic shared
-// memory is padded to 72 KB so that a fourth CTA can never become resident (four CTAs holding 128 columns each and all
-// waiting for their 32 would deadlock).
-// =====================================================================================================================
-namespace v7 {
-constexpr uint32_t kSmemBytes = 72 * 1024;
-constexpr uint32_t kColS = 0, kColO = 64;     // in the 128-column allocation
-constexpr int kRegsAux = 24, kRegsSoftmax = 128;   // 3 x (128 x 128 + 128 x 24) <= 3 x 256 x 80
-}  // namespace v7
-
-struct SoftmaxCtx7 {
-  uint32_t tmem_s, tmem_o, tmem_p;
-  float sl2, thr;
-  uint64_t *s_full, *s_free, *p_full, *pv_done;
-  float m_ref, l;
-};
-
-template <int POLY, bool MASKED>
-__device__ __forceinline__ void softmax_tile7(SoftmaxCtx7& c, int j, int valid, long long* tph, bool timing, long long& tprev) {
-#ifdef WVN_ATTN_TIMING
-#define WVN_TPH(i) if (timing) { const long long tn = clock64(); tph[i] += tn - tprev; tprev = tn; }
-#else
-#define WVN_TPH(i)
-#endif
-  mbar_wait(c.s_full, j & 1);
-  tc_fence_after();
-  WVN_TPH(0)
-  uint32_t sr[2][32];
-  tmem_ld32(c.tmem_s, sr[0]);
-  tmem_ld_wait();
-  tmem_ld32(c.tmem_s + 32, sr[1]);
-  float mx;
-  if (!MASKED) {
-    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      m0 = max3(m0, __uint_as_float(sr[0][i]), __uint_as_float(sr[0][i + 1]));
-      m1 = max3(m1, __uint_as_float(sr[0][i + 2]), __uint_as_float(sr[0][i + 3]));
-      m2 = max3(m2, __uint_as_float(sr[0][i + 4]), __uint_as_float(sr[0][i + 5]));
-      m3 = max3(m3, __uint_as_float(sr[0][i + 6]), __uint_as_float(sr[0][i + 7]));
-    }
-    tmem_ld_wait();
-    tmem_ld_fence32(sr[1]);
-    tc_fence_before();
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(c.s_free);   // scores in registers: Q·K^T(j+1) may overwrite S
-    WVN_TPH(1)
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      m0 = max3(m0, __uint_as_float(sr[1][i]), __uint_as_float(sr[1][i + 1]));
-      m1 = max3(m1, __uint_as_float(sr[1][i + 2]), __uint_as_float(sr[1][i + 3]));
-      m2 = max3(m2, __uint_as_float(sr[1][i + 4]), __uint_as_float(sr[1][i + 5]));
-      m3 = max3(m3, __uint_as_float(sr[1][i + 6]), __uint_as_float(sr[1][i + 7]));
-    }
-    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-  } else {
-    tmem_ld_wait();
-    tmem_ld_fence32(sr[1]);
-    tc_fence_before();
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(c.s_free);
-    WVN_TPH(1)
-    mx = -INFINITY;
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-#pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (q * 32 + i < valid) ? __uint_as_float(sr[q][i]) : -INFINITY);
-  }
-  bool waited_pv = false;
-  if (j == 0) {
-    c.m_ref = mx;
-  } else {
-    const float m_new = fmaxf(c.m_ref, mx);
-    const bool need = (m_new - c.m_ref) * c.sl2 > c.thr;
-    if (__any_sync(0xffffffffu, need)) {
-      mbar_wait(c.pv_done, (j - 1) & 1);   // O must be quiescent
-      waited_pv = true;
-      tc_fence_after();
-      const float alpha = need ? fast_exp2((c.m_ref - m_new) * c.sl2) : 1.f;
-      if (need) c.m_ref = m_new;
-      c.l *= alpha;
-#pragma unroll 1
-      for (int q = 0; q < 2; ++q) {
-        uint32_t r[32];
-        tmem_ld32(c.tmem_o + q * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-        tmem_st32(c.tmem_o + q * 32, r);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-    }
-  }
-  WVN_TPH(2)
-
-  const float mb2 = c.m_ref * c.sl2;
-  if (!MASKED) {
-    const uint64_t sl2_2 = pack2(c.sl2, c.sl2), nmb2 = pack2(-mb2, -mb2);
-    uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint32_t pr[16];
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const uint64_t x2 = fma2(pack2(__uint_as_float(sr[q][i]), __uint_as_float(sr[q][i + 1])), sl2_2, nmb2);
-        float e0, e1;
-        if (POLY == 9) {
-          unpack2(x2, e0, e1);
-        } else if (((i >> 1) & 7) < POLY) {
-          poly_exp2_pair(x2, e0, e1);
-        } else {
-          float x0, x1;
-          unpack2(x2, x0, x1);
-          e0 = fast_exp2(x0);
-          e1 = fast_exp2(x1);
-        }
-        if ((i >> 1) & 1) lb = add2(lb, pack2(e0, e1)); else la = add2(la, pack2(e0, e1));
-        pr[i >> 1] = pack_bf16x2(e0, e1);
-      }
-      if (q == 0 && j > 0 && !waited_pv) {   // P·V(j-1) has read the P columns
-        mbar_wait(c.pv_done, (j - 1) & 1);
-        tc_fence_after();
-      }
-      tmem_st16(c.tmem_p + q * 16, pr);
-    }
-    float s0, s1;
-    unpack2(add2(la, lb), s0, s1);
-    c.l += s0 + s1;
-  } else {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint32_t pr[16];
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const int col = q * 32 + i;
-        const float e0 = (col < valid) ? fast_exp2(fmaf(__uint_as_float(sr[q][i]), c.sl2, -mb2)) : 0.f;
-        const float e1 = (col + 1 < valid) ? fast_exp2(fmaf(__uint_as_float(sr[q][i + 1]), c.sl2, -mb2)) : 0.f;
-        c.l += e0 + e1;
-        pr[i >> 1] = pack_bf16x2(e0, e1);
-      }
-      if (q == 0 && j > 0 && !waited_pv) {
-        mbar_wait(c.pv_done, (j - 1) & 1);
-        tc_fence_after();
-      }
-      tmem_st16(c.tmem_p + q * 16, pr);
-    }
-  }
-  WVN_TPH(3)
-  tmem_st_wait();
-  tc_fence_before();
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(c.p_full);
-  WVN_TPH(4)
-#undef WVN_TPH
-}
-
-template <int POLY>
-__global__ void __launch_bounds__(v5::kThreads, 3)
-attention7_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                  const __grid_constant__ CUtensorMap tmap_vt, const AttnArgs args) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + v5::kOffBar);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = k_full + v5::kStages;
-  uint64_t* v_full = k_empty + v5::kStages;
-  uint64_t* v_empty = v_full + v5::kStages;
-  uint64_t* s_full = v_empty + v5::kStages;
-  uint64_t* s_free = s_full + 1;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* pv_done = s_full + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);   // [0] the 128-column block, [1] the 32-column block
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q_tile = args.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
-  const int bh = args.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
-  const int nkv = (args.n_valid + v5::kTileKV - 1) / v5::kTileKV;
-
-  if (warp == v5::kWarpMma && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < v5::kStages; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 4);
-    mbar_init(p_full, 4);
-    mbar_init(pv_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == v5::kWarpTma) {
-    tmem_alloc_keep_permit(tmem_slot, 128);
-    tmem_alloc_keep_permit(tmem_slot + 1, 32);
-    tmem_relinquish_permit();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_a = tmem_slot[0], tmem_b = tmem_slot[1];
-
-  if (warp == v5::kWarpTma) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(v7::kRegsAux));
-    const int row0 = bh * args.npad;
-    if (elect_one_sync()) {
-      tma_prefetch_desc(&tmap_q);
-      tma_prefetch_desc(&tmap_k);
-      tma_prefetch_desc(&tmap_vt);
-      mbar_arrive_expect_tx(q_full, kQBytes);
-      tma_load_2d(&tmap_q, q_full, smem + kOffQ, 0, row0 + q_tile * kTileQ);
-    }
-    __syncwarp();
-    for (int j = 0; j < nkv; ++j) {
-      const int st = j % v5::kStages;
-      const uint32_t ph = (j / v5::kStages) & 1;
-      mbar_wait(&k_empty[st], ph ^ 1);
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&k_full[st], v5::kKBytes);
-        tma_load_2d(&tmap_k, &k_full[st], smem + v5::kOffK + st * v5::kKBytes, 0, row0 + j * v5::kTileKV);
-      }
-      __syncwarp();
-      mbar_wait(&v_empty[st], ph ^ 1);
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&v_full[st], v5::kVBytes);
-        tma_load_2d(&tmap_vt, &v_full[st], smem + v5::kOffV + st * v5::kVBytes, j * v5::kTileKV, bh * kDh);
-      }
-      __syncwarp();
-    }
-  } else if (warp == v5::kWarpMma) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(v7::kRegsAux));
-    constexpr uint32_t idesc = make_idesc_bf16(kTileQ, 64);
-    const uint32_t tmem_s = tmem_a + v7::kColS;
-    const uint32_t tmem_o = tmem_a + v7::kColO;
-    const uint64_t desc_q = make_sw128_kmajor_desc(smem_u32(smem + kOffQ));
-    auto issue_qk = [&](int j) {
-      const int st = j % v5::kStages;
-      const uint32_t ph = (j / v5::kStages) & 1;
-      mbar_wait(&k_full[st], ph);
-      if (j > 0) mbar_wait(s_free, (j - 1) & 1);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint64_t desc_k = make_sw128_kmajor_desc(smem_u32(smem + v5::kOffK + st * v5::kKBytes));
-#pragma unroll
-        for (int k = 0; k < kDh / 16; ++k) umma_bf16_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc, k != 0);
-        umma_commit(&k_empty[st]);
-        umma_commit(s_full);
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    issue_qk(0);
-    for (int j = 0; j < nkv; ++j) {
-      if (j + 1 < nkv) issue_qk(j + 1);
-      const int st = j % v5::kStages;
-      const uint32_t ph = (j / v5::kStages) & 1;
-      mbar_wait(p_full, j & 1);
-      mbar_wait(&v_full[st], ph);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint64_t desc_v = make_sw128_kmajor_desc(smem_u32(smem + v5::kOffV + st * v5::kVBytes));
-#pragma unroll
-        for (int ks = 0; ks < v5::kTileKV / 16; ++ks)
-          umma_bf16_ts(tmem_o, tmem_b + 8 * ks, desc_v + 2 * ks, idesc, (j | ks) != 0);
-        umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
-      }
-      __syncwarp();
-    }
-  } else if (warp >= 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(v7::kRegsAux));
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(v7::kRegsSoftmax));
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    SoftmaxCtx7 c;
-    c.tmem_s = tmem_a + lane_base + v7::kColS;
-    c.tmem_o = tmem_a + lane_base + v7::kColO;
-    c.tmem_p = tmem_b + lane_base;
-    c.sl2 = args.scale_log2;
-    c.thr = args.rescale_log2;
-    c.s_full = s_full; c.s_free = s_free; c.p_full = p_full; c.pv_done = pv_done;
-    c.m_ref = -INFINITY;
-    c.l = 0.f;
-#ifdef WVN_ATTN_TIMING
-    const bool timing = args.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
-    long long tph[6] = {0, 0, 0, 0, 0, 0}, tprev = timing ? clock64() : 0;
-#else
-    constexpr bool timing = false;
-    long long* tph = nullptr;
-    long long tprev = 0;
-#endif
-    const int tail = args.n_valid - (nkv - 1) * v5::kTileKV;
-#pragma unroll 1
-    for (int j = 0; j < nkv - 1; ++j) softmax_tile7<POLY, false>(c, j, v5::kTileKV, tph, timing, tprev);
-    if (tail == v5::kTileKV) softmax_tile7<POLY, false>(c, nkv - 1, tail, tph, timing, tprev);
-    else softmax_tile7<(POLY == 9 ? 9 : 0), true>(c, nkv - 1, tail, tph, timing, tprev);
-#ifdef WVN_ATTN_TIMING
-    if (timing)
-      for (int i = 0; i < 6; ++i) args.timing[i] = tph[i];
-#endif
-    const float inv_l = 1.f / c.l;
-    mbar_wait(pv_done, (nkv - 1) & 1);
-    tc_fence_after();
-    const int b = bh / args.heads;
-    const int h = bh - b * args.heads;
-    const long long q_idx = static_cast<long long>(b) * args.npad + q_tile * kTileQ + warp * 32 + lane;
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(args.out) + q_idx * args.ldo + h * kDh;
-#pragma unroll 1
-    for (int q = 0; q < 2; ++q) {
-      uint32_t r[32];
-      tmem_ld32(c.tmem_o + q * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i4 = 0; i4 < 4; ++i4) {
-        float f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[8 * i4 + i]) * inv_l;
-        st_global_v4(dst + q * 32 + 8 * i4, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                     pack_bf16x2(f[6], f[7]));
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == v5::kWarpTma) {
-    tc_fence_after();
-    tmem_dealloc(tmem_a, 128);
-    tmem_dealloc(tmem_b, 32);
-  }
-}
-
-
 }  // namespace
 
 int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* vt, cudaStream_t stream) {
@@ -1927,7 +1585,7 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
   if (impl < 0) {
     const char* e = getenv("WVN_ATTN_IMPL");
     impl = e ? atoi(e) : 5;
-    if (impl != 1 && impl != 2 && impl != 3 && impl != 5 && impl != 7) impl = 5;
+    if (impl != 1 && impl != 2 && impl != 3 && impl != 5) impl = 5;
   }
   static int no_token = -1;  // $WVN_ATTN_TOKEN=0: let the two softmax warpgroups free-run (A/B of the exp-phase ordering)
   if (no_token < 0) {
@@ -1945,10 +1603,10 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
   a2.rescale_log2 = rescale;
   const int ntiles = a.npad / kTileQ;
   dim3 grid(impl == 2 ? (ntiles + 1) / 2 : ntiles, static_cast<unsigned>(bh));
-  const bool four = impl == 5 || impl == 7;   // 64-key tile geometry
+  const bool four = impl == 5;
   const int threads = impl == 2 ? v2::kThreads : (impl == 3 ? v3::kThreads : (four ? v5::kThreads : kThreads));
   const uint32_t smem_bytes =
-      impl == 2 ? v2::kSmemBytes : (impl == 3 ? v3::kSmemBytes : (impl == 7 ? v7::kSmemBytes : (four ? v5::kSmemBytes : kSmemBytes)));
+      impl == 2 ? v2::kSmemBytes : (impl == 3 ? v3::kSmemBytes : (four ? v5::kSmemBytes : kSmemBytes));
   if (four) WVN_PROPAGATE(make_tmap_bf16_2d(&tk, k, kDh, bh * a.npad, kDh * 2, 64, v5::kTileKV));   // 64-key K boxes
   auto launch = [&](auto kern) -> int {
     WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -1965,15 +1623,6 @@ int attention_bf16(const AttnArgs& a, const void* q, const void* k, const void* 
       case 3: WVN_PROPAGATE(launch(attention2_kernel<3>)); break;
       case 4: WVN_PROPAGATE(launch(attention2_kernel<4>)); break;
       default: WVN_PROPAGATE(launch(attention2_kernel<9>)); break;
-    }
-  } else if (impl == 7) {
-    switch (poly) {
-      case 0: WVN_PROPAGATE(launch(attention7_kernel<0>)); break;
-      case 1: WVN_PROPAGATE(launch(attention7_kernel<1>)); break;
-      case 2: WVN_PROPAGATE(launch(attention7_kernel<2>)); break;
-      case 3: WVN_PROPAGATE(launch(attention7_kernel<3>)); break;
-      case 4: WVN_PROPAGATE(launch(attention7_kernel<4>)); break;
-      default: WVN_PROPAGATE(launch(attention7_kernel<9>)); break;
     }
   } else if (impl == 5) {
     switch (poly) {
