@@ -52,7 +52,7 @@ constexpr int kMaxStages = 8;
 
 // Per-warp transpose tile of the staged epilogues: 32 rows x 32 columns of the output type.
 __host__ __device__ constexpr int epi_buf_bytes(int epi) {
-  return (epi == EPI_F32 || epi == EPI_RESID_F32) ? 4096 : (epi == EPI_BF16 || epi == EPI_QKV) ? 2048 : 0;
+  return (epi == EPI_F32 || epi == EPI_RESID_F32 || epi == EPI_PATCH) ? 4096 : (epi == EPI_BF16 || epi == EPI_QKV) ? 2048 : 0;
 }
 __host__ __device__ constexpr int fixed_smem_bytes(int epi) {
   return 1024 /*barriers + scratch*/ + kEpiWarps * epi_buf_bytes(epi) + 1024 /*align slack*/;
@@ -226,14 +226,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
     // different 128-byte line (measured 7.6k-19k clk/tile of epilogue against 2.3k clk of MMA) — and
     // TMA stores queue behind the mainloop's in-flight TMA loads.  The residual stream is updated
     // with vector reductions (red.global.add.v4.f32): x += acc + bias happens at L2, no load.
-    constexpr bool kStagedEpi = (EPI == EPI_BF16 || EPI == EPI_F32 || EPI == EPI_RESID_F32 || EPI == EPI_QKV);
+    constexpr bool kStagedEpi = (EPI == EPI_BF16 || EPI == EPI_F32 || EPI == EPI_RESID_F32 || EPI == EPI_QKV || EPI == EPI_PATCH);
     bool qkv_is_v = false;
     if (EPI == EPI_QKV) qkv_is_v = (col0 >= 2 * args.dim);
     if (kStagedEpi && !qkv_is_v) {
       const uint32_t buf = smem_u32(epi_stage) + ewarp * epi_buf_bytes(EPI);
       const int row_base = m_blk * BM + quarter * 32;
       __syncwarp();  // the previous chunk's read-back is complete
-      if (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
+      if (EPI == EPI_F32 || EPI == EPI_RESID_F32 || EPI == EPI_PATCH) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)  // 128-byte rows: 16-byte chunk q of row r lives at q ^ (r & 7)
           sts128(buf + lane * 128 + ((q ^ (lane & 7)) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
@@ -246,6 +246,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
           const int r = it * 4 + (lane >> 3);
           const uint4 val = lds128(buf + r * 128 + ((q ^ (r & 7)) << 4));
           if (row_base + r < args.M WVN_DBG_STORE) {
+            if (EPI == EPI_PATCH) {
+              // patch row -> token row (frame * npad + 1 + token) of the residual stream, plus the position embedding
+              // (round 1 stored these rows lane by lane: 134 us for the patch-embed GEMM, LSU-wavefront bound)
+              const int grow = row_base + r;
+              const int fr = grow / args.tokens_in, tk = grow - fr * args.tokens_in;
+              const float4 pe = __ldg(reinterpret_cast<const float4*>(args.pos + static_cast<long long>(1 + tk) * args.ldo + col0) + q);
+              float4 o4 = make_float4(__uint_as_float(val.x) + pe.x, __uint_as_float(val.y) + pe.y,
+                                      __uint_as_float(val.z) + pe.z, __uint_as_float(val.w) + pe.w);
+              *reinterpret_cast<float4*>(outp + (static_cast<long long>(fr) * args.npad + 1 + tk) * args.ldo + col0 + q * 4) = o4;
+              continue;
+            }
             float* dst = outp + static_cast<long long>(row_base + r) * args.ldo + col0 + q * 4;
             if (EPI == EPI_RESID_F32) {
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(val.x)),
@@ -289,14 +300,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, const uint32
     WVN_ETM(3)
     if (!row_ok) {
       // out-of-range tail row: no per-row work below
-    } else if (EPI == EPI_PATCH) {
-      const float4* p4 = reinterpret_cast<const float4*>(args.pos + static_cast<long long>(1 + tok) * args.ldo + col0);
-      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + out_row * args.ldo + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 p = __ldg(p4 + j);
-        dst[j] = make_float4(v[4 * j] + p.x, v[4 * j + 1] + p.y, v[4 * j + 2] + p.z, v[4 * j + 3] + p.w);
-      }
     } else if (EPI == EPI_MLP_HEAD) {
       // columns [0, feat) = reconstruction of x, column trav_col = traversability logit
       if (col0 < args.feat) {
