@@ -435,7 +435,7 @@ int vit_forward_impl(wvn_vit_t* h, const void* img, bool u8_hwc, int src_batch, 
       sub_attn_env = e ? atoi(e) : kDefaultSubAttn;
       if (sub_attn_env < 1) sub_attn_env = 1 << 30;
     }
-    const int sub_a = std::min(std::min(sub_attn_env, sub), nb);
+    const int sub_a = std::min(sub_attn_env, nb);   // independent of `sub`: attention wants the whole chunk (8.1 waves of CTAs)
     for (int l = 0; l < c.depth; ++l) {
       const std::string b = "blocks." + std::to_string(l) + ".";
       for (int s0 = 0; s0 < nb; s0 += sub_a) {
