@@ -26,8 +26,8 @@
 //      shared memory; nearest centroid -> assign[] (shared)
 //   2. one warp = one patch at a time (lane = channel): the row is added to a WARP-PRIVATE copy of the K x C sums — no
 //      atomics (shared-memory float atomics are CAS loops on sm_100, and large clusters are hot spots), deterministic
-//   3. the warp copies are summed, the CTA's partial sums go to global memory; after one cluster barrier
-//      (release / acquire) every CTA adds the 8 partials in the same order and updates its own copy of the centroids.
+//   3. the warp copies are summed, the CTA's partial sums go to global memory; after one team barrier
+//      (release / acquire) every CTA adds the team's partials in the same order and updates its own copy of the centroids.
 #include "common.cuh"
 #include "host_common.h"
 #include "stego_kmeans.h"
