@@ -47,7 +47,6 @@ struct GemmArgs {
   float cg_std_factor = 0.5f;
   // launch control
   int max_ctas = 0;             // 0 = one CTA per SM
-  int b_resident = 0, a_stages = 0;  // set by the CTA-pair launcher: weight half-slab resident in smem, A ring depth
   int reverse_m = 0;            // walk the m-blocks last-to-first (start on the rows the producer kernel wrote last: L2 hits)
   int debug = 0;                // debug (-DWVN_GEMM_TIMING builds): 1 = skip the global stores, 2 = skip the epilogue body
   long long* timing = nullptr;  // debug (-DWVN_GEMM_TIMING builds): phase cycle counters of CTA 0

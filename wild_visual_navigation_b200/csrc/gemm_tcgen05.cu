@@ -49,7 +49,6 @@ constexpr int kNumEpiThreads = kEpiWarps * 32;
 constexpr int kNumThreads = (4 + kEpiWarps) * 32;
 constexpr int kMaxSmemBytes = 227 * 1024;
 constexpr int kMaxStages = 8;
-constexpr int kDefaultPairMask = 0;   // epilogues on the CTA-pair kernel by default (see pair_mask()); set from measurements
 
 // Per-warp transpose tile of the staged epilogues: 32 rows x 32 columns of the output type.
 __host__ __device__ constexpr int epi_buf_bytes(int epi) {
@@ -552,262 +551,6 @@ int launch_gemm(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
   return WVN_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// CTA-pair kernel: 256 x BN tiles on tcgen05.mma.cta_group::2 (a 2-CTA cluster = the two SMs of a TPC).  Each CTA
-// stages only its own 128 rows of A and its own BN / 2 rows of W, so the L2 -> SM operand bytes per flop — what bounds
-// the single-CTA mainloop at these skinny-K shapes (§3.1) — drop by a third; with K = 384 each CTA's half of the
-// [BN, K] weight slab stays RESIDENT in shared memory and only activations stream.  Round 1 built this kernel with
-// single-lane role loops and measured it 5-10 % slower than the single-CTA kernel; round 2 found that such loops make
-// ptxas serialise every tcgen05 / TMA instruction (elect_one_sync, common.cuh) — the leader's MMA issuer was the
-// bottleneck, not the handshakes.  Here every role loop runs warp-wide and issues under elect.sync.
-//   shared memory per CTA:  [ W half-slab (resident: K/64 k-blocks | streaming: ring) ][ A ring ][ barriers ][ epilogue ]
-//   barriers: full[s]   leader only, 1 arrival (its expect_tx) + the bytes of BOTH CTAs' loads
-//             empty[s]  each CTA, signalled by the leader's multicast tcgen05.commit
-//             acc_full  each CTA (multicast commit);  acc_empty  leader only, 2 x kEpiWarps warp-arrivals
-//             b_full    leader only (resident slab landed);  b_empty  each CTA (slab may be overwritten)
-// ------------------------------------------------------------------------------------------------
-struct PairIter {
-  int lin, end, stride, num_n, n_fixed;
-  bool resident;
-  __device__ PairIter(int num_mp, int nn, bool res) : num_n(nn), n_fixed(0), resident(res) {
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    if (resident) { n_fixed = pair % nn; lin = pair / nn; stride = npairs / nn; end = num_mp; }
-    else { lin = pair; stride = npairs; end = num_mp * nn; }
-  }
-  __device__ bool valid() const { return lin < end; }
-  __device__ void next() { lin += stride; }
-  __device__ int mp() const { return resident ? lin : lin / num_n; }
-  __device__ int n() const { return resident ? n_fixed : lin % num_n; }
-};
-
-template <int BN, int EPI, int ACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmArgs args) {
-  using Cfg = GemmCfg<BN, EPI>;
-  constexpr uint32_t kBHalfBytes = (BN / 2) * BK * 2;
-  const bool resident = args.b_resident != 0;
-  const int STAGES = args.a_stages;
-  const int num_k = args.K / BK;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_b = smem;
-  uint8_t* smem_a = smem + static_cast<uint32_t>(resident ? num_k : STAGES) * kBHalfBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + STAGES * Cfg::kABytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kMaxStages;
-  uint64_t* acc_full = bars + 2 * kMaxStages;
-  uint64_t* acc_empty = bars + 2 * kMaxStages + 2;
-  uint64_t* b_full = bars + 2 * kMaxStages + 4;
-  uint64_t* b_empty = bars + 2 * kMaxStages + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int crank = static_cast<int>(cluster_ctarank());
-  const bool leader = crank == 0;
-
-  const int num_m = (args.M + BM - 1) / BM;
-  const int num_mp = (num_m + 1) / 2;
-  const int num_n = args.N / BN;
-
-  if (warp == kWarpTma && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-  }
-  if (warp == kWarpMma && lane == 0) {
-    for (int i = 0; i < kMaxStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 2 * kEpiWarps);
-    }
-    mbar_init(b_full, 1);
-    mbar_init(b_empty, 1);
-    fence_mbar_init();
-  }
-  if (warp == kWarpAlloc) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / complete_tx
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  auto m_of = [&](int mp) { return 2 * (args.reverse_m ? num_mp - 1 - mp : mp) + crank; };
-
-  if (warp == kWarpTma) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs; warp-wide loop, one
-    // elected lane issues)
-    int stage = 0, cur_n = -1;
-    uint32_t phase = 0, be_phase = 0;
-    for (PairIter it(num_mp, num_n, resident); it.valid(); it.next()) {
-      const int n = it.n();
-      const int b_row = n * BN + crank * (BN / 2);
-      if (resident && n != cur_n) {
-        if (cur_n >= 0) { mbar_wait(b_empty, be_phase); be_phase ^= 1; }  // every MMA on the old slab retired
-        if (elect_one_sync()) {
-          if (leader) mbar_arrive_expect_tx(b_full, 2u * static_cast<uint32_t>(num_k) * kBHalfBytes);
-          for (int kb = 0; kb < num_k; ++kb)
-            tma_load_2d_pair(&tmap_b, leader_smem_addr(b_full), smem_b + kb * kBHalfBytes, kb * BK, b_row);
-        }
-        __syncwarp();
-        cur_n = n;
-      }
-      const int m_blk = m_of(it.mp());
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (elect_one_sync()) {
-          const uint32_t full_l = leader_smem_addr(&full_bar[stage]);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * (Cfg::kABytes + (resident ? 0u : kBHalfBytes)));
-          tma_load_2d_pair(&tmap_a, full_l, smem_a + stage * Cfg::kABytes, kb * BK, m_blk * BM);
-          if (!resident) tma_load_2d_pair(&tmap_b, full_l, smem_b + stage * kBHalfBytes, kb * BK, b_row);
-        }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == kWarpMma) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
-      int stage = 0, acc = 0, cur_n = -1;
-      uint32_t phase = 0, acc_phase = 0, bf_phase = 0;
-      for (PairIter it(num_mp, num_n, resident); it.valid(); it.next()) {
-        const int n = it.n();
-        if (resident && n != cur_n) { mbar_wait(b_full, bf_phase); bf_phase ^= 1; cur_n = n; }
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        PairIter nx = it;
-        nx.next();
-        const bool slab_done = resident && nx.valid() && nx.n() != n;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (elect_one_sync()) {
-            const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
-            const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + (resident ? kb : stage) * kBHalfBytes));
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16_ss_pair(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit_pair(&empty_bar[stage], 3);  // both CTAs' producers may refill the slot
-            if (kb == num_k - 1) {
-              umma_commit_pair(&acc_full[acc], 3);  // accumulator complete -> both CTAs' epilogues
-              if (slab_done) umma_commit_pair(b_empty, 3);  // slab free once this tile's MMAs retire
-            }
-          }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
-    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
-    const int ewarp = warp - kEpiWarp0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    float unused = 0.f;
-    for (PairIter it(num_mp, num_n, resident); it.valid(); it.next()) {
-      float bias_lane[EpiChunks<BN>::kPerThread];
-      epilogue_prefetch_bias<BN>(args, it.n(), ewarp, lane, bias_lane);
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
-      epilogue_tile<BN, EPI, ACT>(args, tmem_base + acc * BN, m_of(it.mp()), it.n(), ewarp, lane, epi_stage, unused, bias_lane);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(leader_smem_addr(&acc_empty[acc]));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers / TMEM
-  if (warp == kWarpAlloc) {
-    tc_fence_after();
-    tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
-  }
-}
-
-// Pair-kernel geometry for a [N, K] weight: the half-slab stays resident when it leaves room for at least 4 activation
-// stages.
-struct PairPlan {
-  bool resident;
-  int a_stages;
-  uint32_t smem_bytes;
-};
-
-PairPlan plan_pair(int block_n, int K, int epi, bool allow_resident) {
-  const int half = (block_n / 2) * BK * 2;
-  const int slab = (K / BK) * half;
-  const int budget = kMaxSmemBytes - fixed_smem_bytes(epi);
-  PairPlan p;
-  p.resident = allow_resident && slab + 4 * BM * BK * 2 <= budget;
-  p.a_stages = p.resident ? (budget - slab) / (BM * BK * 2) : budget / (BM * BK * 2 + half);
-  if (p.a_stages > kMaxStages) p.a_stages = kMaxStages;
-  p.smem_bytes = static_cast<uint32_t>(p.resident ? slab + p.a_stages * BM * BK * 2 : p.a_stages * (BM * BK * 2 + half)) +
-                 fixed_smem_bytes(epi);
-  return p;
-}
-
-template <int BN, int EPI, int ACT>
-int launch_gemm_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
-  auto kern = gemm_pair_kernel<BN, EPI, ACT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes));
-    attr_set = true;
-  }
-  const int num_m = (a.M + BM - 1) / BM, num_mp = (num_m + 1) / 2, num_n = a.N / BN;
-  const long long items = static_cast<long long>(num_mp) * num_n;
-  long long pairs = sm_count() / 2;
-  if (a.max_ctas > 0 && a.max_ctas / 2 < pairs) pairs = std::max(1, a.max_ctas / 2);
-  if (pairs > items) pairs = items;
-  PairPlan plan = plan_pair(BN, a.K, EPI, true);
-  if (plan.resident) {
-    if (pairs / num_n >= 1) pairs = (pairs / num_n) * num_n;  // S slots x num_n pinned n-blocks
-    else plan = plan_pair(BN, a.K, EPI, false);
-  }
-  GemmArgs la = a;
-  la.b_resident = plan.resident ? 1 : 0;
-  la.a_stages = plan.a_stages;
-  prof_begin(PROF_GEMM, stream);
-  kern<<<static_cast<unsigned>(2 * pairs), kNumThreads, plan.smem_bytes, stream>>>(ta, tb, la);
-  prof_end(PROF_GEMM, stream);
-  WVN_CHECK_LAUNCH("gemm_pair_kernel");
-  return WVN_OK;
-}
-
-// $WVN_GEMM_PAIR: bit mask of the epilogues that use the CTA-pair kernel (1 QKV, 2 bf16 (+ activation), 4 residual, 8 fp32).
-int pair_mask() {
-  static int mask = -1;
-  if (mask < 0) {
-    const char* e = getenv("WVN_GEMM_PAIR");
-    mask = e ? atoi(e) : kDefaultPairMask;
-  }
-  return mask;
-}
-
-template <int BN>
-int dispatch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t s) {
-  switch (a.epi) {
-    case EPI_BF16:
-      if (a.act == ACT_NONE) return launch_gemm_pair<BN, EPI_BF16, ACT_NONE>(a, ta, tb, s);
-      if (a.act == ACT_RELU) return launch_gemm_pair<BN, EPI_BF16, ACT_RELU>(a, ta, tb, s);
-      if (a.act == ACT_GELU) return launch_gemm_pair<BN, EPI_BF16, ACT_GELU>(a, ta, tb, s);
-      break;
-    case EPI_F32: return launch_gemm_pair<BN, EPI_F32, ACT_NONE>(a, ta, tb, s);
-    case EPI_RESID_F32: return launch_gemm_pair<BN, EPI_RESID_F32, ACT_NONE>(a, ta, tb, s);
-    case EPI_QKV: return launch_gemm_pair<BN, EPI_QKV, ACT_NONE>(a, ta, tb, s);
-    default: break;
-  }
-  return set_error(WVN_ERR_INVALID, "gemm: the CTA-pair kernel has no epilogue %d", a.epi);
-}
-
 template <int BN>
 int dispatch_epi(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t s) {
   switch (a.epi) {
@@ -865,21 +608,6 @@ int gemm_bf16(const GemmArgs& a, const void* A, long long lda, const void* W, in
   if (a.epi == EPI_BF16) WVN_REQUIRE(a.ldo % 8 == 0, "gemm: bf16 output pitch must be a multiple of 8");
   CUtensorMap ta, tb;
   WVN_PROPAGATE(make_tmap_bf16_2d(&ta, A, a.K, a.M, static_cast<uint64_t>(lda) * 2, BK, BM));
-  // CTA-pair kernel: for the epilogues enabled in pair_mask(), when the problem has at least one 256-row item per pair
-  // of SMs and a pair-capable tile width (both halves a whole number of 8-row swizzle groups)
-  {
-    const int bit = a.epi == EPI_QKV ? 1 : a.epi == EPI_BF16 ? 2 : a.epi == EPI_RESID_F32 ? 4 : a.epi == EPI_F32 ? 8 : 0;
-    const int pair_n = (block_n == 256 || block_n == 192 || block_n == 128) ? block_n : 0;
-    const long long items = pair_n ? static_cast<long long>(((a.M + BM - 1) / BM + 1) / 2) * (a.N / pair_n) : 0;
-    if ((pair_mask() & bit) && pair_n && items >= sm_count() / 2 && a.max_ctas == 0) {
-      WVN_PROPAGATE(make_tmap_bf16_2d(&tb, W, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, pair_n / 2));
-      switch (pair_n) {
-        case 128: return dispatch_pair<128>(a, ta, tb, stream);
-        case 192: return dispatch_pair<192>(a, ta, tb, stream);
-        case 256: return dispatch_pair<256>(a, ta, tb, stream);
-      }
-    }
-  }
   WVN_PROPAGATE(make_tmap_bf16_2d(&tb, W, a.K, a.N, static_cast<uint64_t>(a.K) * 2, BK, block_n));
   switch (block_n) {
     case 64: return dispatch_epi<64>(a, ta, tb, stream);
