@@ -166,6 +166,11 @@ int wvn_logits_argmax(const float* logits, long long ld, int col0, int classes, 
  * [logit_col, logit_col+k) so that wvn_logits_argmax yields the per-pixel labels of the upsampled code.
  * centroids_out: optional [batch, k, code_dim]; workspace: wvn_stego_kmeans_workspace_bytes(batch, k, code_dim) bytes of device
  * memory (partial sums of the 8 CTAs that share a frame; no initialisation needed).  One launch for all frames and iterations. */
+/* STEGO's flip test-time augmentation (Stego.get_code: the code of the image and of its horizontal flip are averaged):
+ * head [2*batch*npad, ld] holds the head output of the straight pass (frames [0, batch)) and of the pass over the flipped
+ * transformed images (frames [batch, 2*batch), see wvn_vit_forward_tta).  In place: rows of the straight pass become
+ * 0.5 * (own + mirrored row of the flipped pass); CLS / padding rows are zeroed. */
+int wvn_flip_average(float* head, int batch, int npad, int grid, long long ld, void* stream);
 size_t wvn_stego_kmeans_workspace_bytes(int batch, int k, int code_dim);
 int wvn_stego_kmeans(float* rows, long long ld, int batch, int npad, int patches, int code_col, int code_dim, int logit_col,
                      int k, int iters, float* centroids_out, void* workspace, void* stream);

@@ -58,6 +58,7 @@ SIGNATURES = {
     "wvn_vit_npad": (_I, [_P]),
     "wvn_upsample_dense": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "wvn_logits_argmax": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "wvn_flip_average": (_I, [_P, _I, _I, _I, _L, _P]),
     "wvn_stego_kmeans_workspace_bytes": (_S, [_I, _I, _I]),
     "wvn_stego_kmeans": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "wvn_segment_workspace_bytes": (_S, [_I, _I, _I, _I]),

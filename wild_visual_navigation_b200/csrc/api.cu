@@ -554,6 +554,10 @@ int wvn_logits_argmax(const float* logits, long long ld, int col0, int classes, 
   return logits_argmax(logits, seg, seg_b, a, S(stream));
 }
 
+int wvn_flip_average(float* head, int batch, int npad, int grid, long long ld, void* stream) {
+  return flip_average(head, batch, npad, grid, ld, S(stream));
+}
+
 size_t wvn_stego_kmeans_workspace_bytes(int batch, int k, int code_dim) { return stego_kmeans_workspace_bytes(batch, k, code_dim); }
 
 int wvn_stego_kmeans(float* rows, long long ld, int batch, int npad, int patches, int code_col, int code_dim, int logit_col,

@@ -15,6 +15,8 @@
 //                           positive per-pixel normalisation.
 #include "common.cuh"
 #include "dense_kernels.h"
+
+#include <algorithm>
 #include "host_common.h"
 
 namespace wvn {
@@ -203,6 +205,36 @@ int logits_argmax(const float* logits, long long* seg, long long* seg_b, const L
   if (blocks > max_blocks) blocks = max_blocks;
   logits_argmax_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(logits, seg, seg_b, a);
   WVN_CHECK_LAUNCH("logits_argmax_kernel");
+  return WVN_OK;
+}
+
+namespace {
+__global__ void __launch_bounds__(256)
+flip_average_kernel(float* __restrict__ head, int batch, int npad, int grid, long long ld) {
+  const long long per_frame = static_cast<long long>(npad) * ld;
+  const long long total = batch * per_frame;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / per_frame, rem = i - b * per_frame;
+    const int row = static_cast<int>(rem / ld), c = static_cast<int>(rem - static_cast<long long>(row) * ld);
+    const int p = row - 1;
+    float v = 0.f;
+    if (p >= 0 && p < grid * grid) {
+      const int y = p / grid, x = p - y * grid;
+      const long long mirrored = (static_cast<long long>(batch + b) * npad + 1 + y * grid + (grid - 1 - x)) * ld + c;
+      v = 0.5f * (head[i] + head[mirrored]);   // the flipped pass's rows are only read
+    }
+    head[i] = v;
+  }
+}
+}  // namespace
+
+int flip_average(float* head, int batch, int npad, int grid, long long ld, cudaStream_t stream) {
+  WVN_REQUIRE(head && batch > 0 && npad > grid * grid && ld > 0, "flip_average: bad arguments");
+  const long long total = static_cast<long long>(batch) * npad * ld;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(sm_count()) * 16));
+  flip_average_kernel<<<blocks, 256, 0, stream>>>(head, batch, npad, grid, ld);
+  WVN_CHECK_LAUNCH("flip_average_kernel");
   return WVN_OK;
 }
 

@@ -31,5 +31,8 @@ int upsample_tokens_dense(const float* tokens, float* out_nchw, const DenseArgs&
 int interp_pixel_rows(const float* tokens, void* out_bf16, const DenseArgs& a, long long pix0, long long npix,
                       cudaStream_t stream);
 int logits_argmax(const float* logits, long long* seg, long long* seg_b, const LogitsArgs& a, cudaStream_t stream);
+// STEGO's flip test-time augmentation: head rows of the straight pass (frames [0, B)) become the mean of themselves and
+// the horizontally mirrored rows of the flipped pass (frames [B, 2B)); CLS / padding rows are zeroed.  head: [2B*npad, ld].
+int flip_average(float* head, int batch, int npad, int grid, long long ld, cudaStream_t stream);
 
 }  // namespace wvn

@@ -88,12 +88,9 @@ class StegoInterface:
             # Stego.get_code: average with the pass over the horizontally flipped TRANSFORMED image (the flip happens
             # inside the patch loader, after resize + crop); flip back at patch level
             tokens = vit.forward(img, flip_tta=True)
-            out = vit.stego_head(2 * B).view(2, B, npad, -1)
-            a = out[0, :, 1 : 1 + g * g].reshape(B, g, g, -1)
-            b = out[1, :, 1 : 1 + g * g].reshape(B, g, g, -1).flip(dims=[2])
-            head = torch.zeros(B, npad, out.shape[-1], device=img.device)
-            head[:, 1 : 1 + g * g] = ((a + b) * 0.5).reshape(B, g * g, -1)
-            head = head.view(B * npad, -1)
+            out = vit.stego_head(2 * B)                                  # [2B * npad, C]: straight pass, then flipped pass
+            ops.flip_average(out, B, npad, g)                            # in place on the straight half (one kernel)
+            head = out[: B * npad]
             self._tokens = tokens[:B]
         else:
             self._tokens = vit.forward(img)

@@ -195,6 +195,12 @@ def project_and_render(sK, pose_camera_in_world, points, colors, h, w, render=Tr
     return masks, proj, valid.bool()
 
 
+def flip_average(head, batch, npad, grid):
+    """STEGO flip-TTA merge of the head output [2*batch*npad, C] in place (see include/wvn_b200.h)."""
+    assert head.is_contiguous() and head.shape[0] == 2 * batch * npad and head.dtype == torch.float32
+    check(lib().wvn_flip_average(ptr(head), batch, npad, grid, head.stride(0), stream()))
+
+
 def stego_kmeans(head, batch, npad, patches, code_col, code_dim, logit_col, k, iters, centroids_out=None):
     """Per-image k-means of the code columns of the head output ``head`` [batch*npad, ld]; leaves the per-patch
     nearest-centroid scores in columns [logit_col, logit_col + k) (see include/wvn_b200.h)."""
