@@ -38,7 +38,14 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kCluster = 9;   // CTAs per frame (a software team, see above): 16 teams = 144 SMs, 32 frames = 2 full rounds
+constexpr int kTeam = 9;       // CTAs per frame at large batches: 16 teams = 144 SMs, 32 frames = 2 full rounds
+constexpr int kMaxTeam = 32;   // small batches (the one-camera deployment case) spread a frame over more CTAs
+
+// CTAs per frame: as many as keep every team resident in ONE round (148 SMs, one CTA each), between kTeam and kMaxTeam.
+inline int team_size(int batch) {
+  const int fit = sm_count() / (batch > 0 ? batch : 1);
+  return fit < kTeam ? kTeam : (fit > kMaxTeam ? kMaxTeam : fit);
+}
 
 // Arrive at the frame's counter and wait until `target` arrivals: release before, acquire after; bounded (traps after
 // ~2 s instead of hanging the GPU if a team member never shows up).
@@ -85,13 +92,14 @@ stego_kmeans_kernel(float* __restrict__ rows, KmeansArgs a, float* __restrict__ 
   float* rows_s = sum_priv + n_priv * K * CP;  // [per][C + 1] (odd row stride: one row per lane is conflict-free)
   __shared__ unsigned char assign[1024];       // per CTA: <= 1024 patches (8 CTAs per frame)
 
-  const uint32_t rank = blockIdx.x % kCluster;
-  const int frame = blockIdx.x / kCluster;
-  const int per = (P + kCluster - 1) / kCluster;
+  const int T = a.team;                       // CTAs of this frame
+  const uint32_t rank = blockIdx.x % T;
+  const int frame = blockIdx.x / T;
+  const int per = (P + T - 1) / T;
   const int p0 = rank * per, p1 = min(P, p0 + per);
   float* base = rows + (static_cast<long long>(frame) * a.npad + 1) * a.ld;  // row 0 of a frame is the CLS token
   auto code = [&](int p) { return base + static_cast<long long>(p) * a.ld + a.code_col; };
-  float* part_frame = partial + static_cast<long long>(frame) * 2 * kCluster * (K * CP + K);  // [2 buffers][8 ranks][K*CP + K]
+  float* part_frame = partial + static_cast<long long>(frame) * 2 * T * (K * CP + K);  // [2 buffers][T ranks][K*CP + K]
   const int RS = C + 1;
   const uint32_t cent_addr = smem_u32(cent);
 
@@ -213,7 +221,7 @@ stego_kmeans_kernel(float* __restrict__ rows, KmeansArgs a, float* __restrict__ 
     __syncthreads();
     WVN_KT(3)
     // ---- 3. CTA partial -> global; team barrier; every CTA sums the team's partials in rank order
-    float* mine = part_frame + ((it & 1) * kCluster + rank) * (K * CP + K);
+    float* mine = part_frame + ((it & 1) * T + rank) * (K * CP + K);
     for (int i = t; i < K * CP + K; i += kThreads) {
       float sacc = 0.f;
       if (i < K * CP) {
@@ -224,16 +232,16 @@ stego_kmeans_kernel(float* __restrict__ rows, KmeansArgs a, float* __restrict__ 
       mine[i] = sacc;
     }
     WVN_KT(4)
-    team_barrier(a.frame_bar + frame, static_cast<unsigned int>(kCluster) * (it + 1));
+    team_barrier(a.frame_bar + frame, static_cast<unsigned int>(T) * (it + 1));
     WVN_KT(5)
-    const float* all = part_frame + (it & 1) * kCluster * (K * CP + K);
+    const float* all = part_frame + (it & 1) * T * (K * CP + K);
     for (int k = warp; k < K; k += kWarps) {  // one warp per centroid
       float n = 0.f;
-      for (int r = 0; r < kCluster; ++r) n += __ldcg(all + r * (K * CP + K) + K * CP + k);
+      for (int r = 0; r < T; ++r) n += __ldcg(all + r * (K * CP + K) + K * CP + k);
       if (n > 0.f) {  // empty cluster: keep its centroid
         for (int c = lane; c < C; c += 32) {
           float sacc = 0.f;
-          for (int r = 0; r < kCluster; ++r) sacc += __ldcg(all + r * (K * CP + K) + k * CP + c);
+          for (int r = 0; r < T; ++r) sacc += __ldcg(all + r * (K * CP + K) + k * CP + c);
           cent[k * CP + c] = sacc / n;
         }
       }
@@ -259,7 +267,7 @@ stego_kmeans_kernel(float* __restrict__ rows, KmeansArgs a, float* __restrict__ 
 
 size_t stego_kmeans_workspace_bytes(int batch, int k, int code_dim) {
   const int CP = code_dim <= 96 ? 96 : 128;
-  return sizeof(float) * static_cast<size_t>(batch) * 2 * kCluster * (static_cast<size_t>(k) * CP + k) +
+  return sizeof(float) * static_cast<size_t>(batch) * 2 * team_size(batch) * (static_cast<size_t>(k) * CP + k) +
          sizeof(unsigned int) * static_cast<size_t>(batch) + 16;
 }
 
@@ -268,11 +276,12 @@ int stego_kmeans(float* rows, const KmeansArgs& a_in, float* workspace, cudaStre
   WVN_REQUIRE(rows && workspace && a.batch > 0 && a.patches > 0, "kmeans: empty problem");
   WVN_REQUIRE(a.k > 0 && a.k <= kMaxK && a.code_dim > 0 && a.code_dim <= kMaxC, "kmeans: k=%d (<= %d), code_dim=%d (<= %d)",
               a.k, kMaxK, a.code_dim, kMaxC);
-  WVN_REQUIRE(a.patches >= a.k && a.patches <= kCluster * 1024 && a.iters >= 0 && a.logit_col % 4 == 0 &&
+  a.team = team_size(a.batch);
+  WVN_REQUIRE(a.patches >= a.k && a.patches <= a.team * 1024 && a.iters >= 0 && a.logit_col % 4 == 0 &&
                   a.logit_col + a.k <= a.ld && (a.logit_col >= a.code_col + a.code_dim || a.logit_col + a.k <= a.code_col),
               "kmeans: bad geometry (patches=%d) / column layout / iteration count", a.patches);
   const int CP = a.code_dim <= 96 ? 96 : 128;
-  const int per = (a.patches + kCluster - 1) / kCluster;
+  const int per = (a.patches + a.team - 1) / a.team;
   const size_t fixed = sizeof(float) * (static_cast<size_t>(a.k) * CP + kMaxK + kWarps * kMaxK);
   const size_t per_copy = sizeof(float) * static_cast<size_t>(a.k) * CP;
   const size_t rows_bytes = sizeof(float) * static_cast<size_t>(per) * (a.code_dim + 1);
@@ -289,7 +298,7 @@ int stego_kmeans(float* rows, const KmeansArgs& a_in, float* workspace, cudaStre
                                : (a.rows_in_smem ? stego_kmeans_kernel<128, true> : stego_kmeans_kernel<128, false>);
   WVN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   // the per-frame arrival counters live behind the partial sums and start from zero
-  const size_t part_floats = static_cast<size_t>(a.batch) * 2 * kCluster * (static_cast<size_t>(a.k) * CP + a.k);
+  const size_t part_floats = static_cast<size_t>(a.batch) * 2 * a.team * (static_cast<size_t>(a.k) * CP + a.k);
   a.frame_bar = reinterpret_cast<unsigned int*>(workspace + ((part_floats + 3) & ~static_cast<size_t>(3)));
   WVN_CHECK_CUDA(cudaMemsetAsync(a.frame_bar, 0, sizeof(unsigned int) * a.batch, stream));
 #ifdef WVN_GEMM_TIMING
@@ -297,7 +306,7 @@ int stego_kmeans(float* rows, const KmeansArgs& a_in, float* workspace, cudaStre
   if (!tbuf) cudaMalloc(&tbuf, 8 * sizeof(long long));
   a.timing = tbuf;
 #endif
-  kern<<<a.batch * kCluster, kThreads, smem, stream>>>(rows, a, workspace);
+  kern<<<a.batch * a.team, kThreads, smem, stream>>>(rows, a, workspace);
   WVN_CHECK_LAUNCH("stego_kmeans_kernel");
 #ifdef WVN_GEMM_TIMING
   {

@@ -18,6 +18,7 @@ struct KmeansArgs {
   long long* timing = nullptr;      // debug (-DWVN_GEMM_TIMING builds): phase cycle counters of CTA 0
   int rows_in_smem = 0;             // set by stego_kmeans(): the CTA's code rows are staged in shared memory
   unsigned int* frame_bar = nullptr;  // set by stego_kmeans(): [batch] arrival counters of the per-frame barrier
+  int team = 0;                       // set by stego_kmeans(): CTAs per frame
 };
 
 // workspace: stego_kmeans_workspace_bytes(batch, k, code_dim) bytes of device memory (per-CTA partial sums).
